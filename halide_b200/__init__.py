@@ -1,0 +1,11 @@
+"""halide_b200 — B200-native drop-in for Halide's canonical apps/ pipelines.
+
+The product is ``libhalide_b200.so``: hand-written sm_100a CUDA kernels behind the exact C ABI a
+Halide AOT filter exports (``int local_laplacian(halide_buffer_t*, int, float, float,
+halide_buffer_t*)`` ...; see ``include/*.h``).  This Python package is only the thin ctypes
+binding the tests and ``bench.py`` use to call that C ABI; it contains no compute and no
+fallback: importing :mod:`halide_b200.lib` raises if the shared library has not been built.
+"""
+from .buffer import HalideBuffer, halide_buffer_t, halide_dimension_t  # noqa: F401
+from .lib import lib, load_library, HalideError, capture_errors  # noqa: F401
+from . import filters  # noqa: F401

@@ -1,0 +1,214 @@
+// blur.cu — halide_blur(input, blur_y): 3x3 box filter on uint16, the plumbing target (config 1).
+//
+// Algorithm (reference: apps/blur/halide_blur_generator.cpp:39-40):
+//   blur_x(x,y) = (in(x,y) + in(x+1,y) + in(x+2,y)) / 3
+//   blur_y(x,y) = (blur_x(x,y) + blur_x(x,y+1) + blur_x(x,y+2)) / 3
+// All arithmetic stays uint16 (Halide's u16+u16 is u16 and wraps, src/IROperator.cpp:769-816), so
+// the sums are taken mod 2^16 before the unsigned divide.  There is no boundary condition: the
+// input must cover [ox, ox+W+1] x [oy, oy+H+1] or the call fails with -4
+// (src/AddImageChecks.cpp:404-417).
+//
+// Kernel shape: HBM-bound, 4 algorithmic bytes per pixel.  One warp owns a 256-pixel-wide
+// column strip; each lane produces 8 adjacent pixels (one 16-byte store) per row and walks down
+// the strip keeping the last three blur_x rows in registers, so every input element is fetched
+// once per strip as part of an aligned 16-byte load and the 2-pixel horizontal apron comes from
+// the neighbouring lane by shuffle, not from memory.
+#include "hb_common.h"
+
+namespace {
+
+constexpr int kPxPerLane = 8;
+constexpr int kStripW = 32 * kPxPerLane;  // 256 output pixels per warp per row
+constexpr int kWarpsPerBlock = 4;
+
+struct BlurArgs {
+    const uint16_t *in;   // element (in_x0, in_y0) of the input == the one feeding output (0,0)
+    uint16_t *out;        // element at output mins
+    int64_t in_stride_y, out_stride_y;
+    int w, h;             // output extent
+    int rows_per_warp;
+    // valid element range of the input allocation relative to `in`, for guarding vector loads
+    int64_t in_lo, in_hi;
+};
+
+__device__ __forceinline__ uint4 load_chunk(const uint16_t *p, int64_t off, int64_t lo, int64_t hi) {
+    // p+off is 16-byte aligned.  Fast path when the whole chunk is inside the allocation span.
+    if (off >= lo && off + 7 <= hi) {
+        return *reinterpret_cast<const uint4 *>(p + off);
+    }
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int64_t e0 = off + 2 * i, e1 = e0 + 1;
+        uint32_t a = (e0 >= lo && e0 <= hi) ? p[e0] : 0u;
+        uint32_t b = (e1 >= lo && e1 <= hi) ? p[e1] : 0u;
+        w[i] = a | (b << 16);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// blur_x for the 8 pixels of this lane on one input row.
+__device__ __forceinline__ void blur_x_row(const BlurArgs &a, int64_t row_off, int x0, int lane, uint32_t bx[8]) {
+    // Element offset (relative to a.in) of the first pixel of this warp's strip on this row.
+    int64_t e = row_off + x0;
+    // Misalignment of that element against 16 bytes, uniform across the warp.
+    int mis = (int)((reinterpret_cast<uintptr_t>(a.in + e) & 15) >> 1);
+    int64_t base = e - mis;  // 16-byte aligned
+    uint4 v = load_chunk(a.in, base + 8 * lane, a.in_lo, a.in_hi);
+    uint4 t = make_uint4(0, 0, 0, 0);
+    if (lane < 2) t = load_chunk(a.in, base + 8 * (32 + lane), a.in_lo, a.in_hi);
+
+    // words of the 3-chunk window: own chunk, next lane's chunk, first word of the chunk after that
+    uint32_t w[9];
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    uint32_t n0 = __shfl_down_sync(0xffffffffu, v.x, 1), n1 = __shfl_down_sync(0xffffffffu, v.y, 1);
+    uint32_t n2 = __shfl_down_sync(0xffffffffu, v.z, 1), n3 = __shfl_down_sync(0xffffffffu, v.w, 1);
+    uint32_t m0 = __shfl_down_sync(0xffffffffu, v.x, 2);
+    uint32_t t0x = __shfl_sync(0xffffffffu, t.x, 0), t0y = __shfl_sync(0xffffffffu, t.y, 0);
+    uint32_t t0z = __shfl_sync(0xffffffffu, t.z, 0), t0w = __shfl_sync(0xffffffffu, t.w, 0);
+    uint32_t t1x = __shfl_sync(0xffffffffu, t.x, 1);
+    if (lane == 31) { n0 = t0x; n1 = t0y; n2 = t0z; n3 = t0w; m0 = t1x; }
+    if (lane == 30) { m0 = t0x; }
+    w[4] = n0; w[5] = n1; w[6] = n2; w[7] = n3; w[8] = m0;
+
+    // 10 halfwords starting at halfword `mis` of the window → 6 words starting at word mis>>1.
+    int wo = mis >> 1;
+    uint32_t s[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        // wo is warp-uniform in [0,3]; select without dynamic register indexing
+        uint32_t c0 = w[i], c1 = w[i + 1], c2 = w[i + 2], c3 = (i + 3 < 9) ? w[i + 3] : 0u;
+        s[i] = wo == 0 ? c0 : wo == 1 ? c1 : wo == 2 ? c2 : c3;
+    }
+    if (mis & 1) {
+#pragma unroll
+        for (int i = 0; i < 5; i++) s[i] = __funnelshift_r(s[i], s[i + 1], 16);
+    }
+    uint32_t px[10];
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        px[2 * i] = s[i] & 0xffffu;
+        px[2 * i + 1] = s[i] >> 16;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        bx[i] = ((px[i] + px[i + 1] + px[i + 2]) & 0xffffu) / 3u;
+    }
+}
+
+__global__ void __launch_bounds__(32 * kWarpsPerBlock) blur3x3_u16_kernel(BlurArgs a) {
+    int lane = threadIdx.x & 31;
+    int warp = threadIdx.x >> 5;
+    int x0 = blockIdx.x * kStripW;
+    int y0 = (blockIdx.y * kWarpsPerBlock + warp) * a.rows_per_warp;
+    if (y0 >= a.h) return;
+    int y1 = min(y0 + a.rows_per_warp, a.h);
+
+    uint32_t r0[8], r1[8], r2[8];
+    blur_x_row(a, (int64_t)y0 * a.in_stride_y, x0, lane, r0);
+    blur_x_row(a, (int64_t)(y0 + 1) * a.in_stride_y, x0, lane, r1);
+    int xl = x0 + lane * kPxPerLane;
+    for (int y = y0; y < y1; y++) {
+        blur_x_row(a, (int64_t)(y + 2) * a.in_stride_y, x0, lane, r2);
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) o[i] = ((r0[i] + r1[i] + r2[i]) & 0xffffu) / 3u;
+        uint16_t *dst = a.out + (int64_t)y * a.out_stride_y + xl;
+        if (xl + 8 <= a.w && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            uint4 pk = make_uint4(o[0] | (o[1] << 16), o[2] | (o[3] << 16), o[4] | (o[5] << 16), o[6] | (o[7] << 16));
+            *reinterpret_cast<uint4 *>(dst) = pk;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (xl + i < a.w) dst[i] = (uint16_t)o[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) { r0[i] = r1[i]; r1[i] = r2[i]; }
+    }
+}
+
+const hb::ArgSpec kIn = {"input", halide_type_uint, 16, 2, false};
+const hb::ArgSpec kOut = {"blur_y", halide_type_uint, 16, 2, true};
+
+const halide_filter_argument_t kArgs[2] = {
+    {"input", halide_argument_kind_input_buffer, 2, {halide_type_uint, 16, 0}, nullptr, nullptr, nullptr, nullptr, nullptr},
+    {"blur_y", halide_argument_kind_output_buffer, 2, {halide_type_uint, 16, 0}, nullptr, nullptr, nullptr, nullptr, nullptr},
+};
+const halide_filter_metadata_t kMeta = {1, 2, kArgs, "x86-64-linux-cuda-cuda_capability_100-b200_native", "halide_blur"};
+
+}  // namespace
+
+extern "C" int halide_blur(halide_buffer_t *input, halide_buffer_t *blur_y) {
+    int r;
+    if ((r = hb::check_arg(input, kIn))) return r;
+    if ((r = hb::check_arg(blur_y, kOut))) return r;
+
+    // Bounds query (src/AddImageChecks.cpp:477-496): the input must cover the output region
+    // grown by the 3-tap footprints: [ox, ox+W+1] x [oy, oy+H+1].
+    const int ox = blur_y->dim[0].min, oy = blur_y->dim[1].min;
+    const int w = blur_y->dim[0].extent, h = blur_y->dim[1].extent;
+    bool query = false;
+    if (hb::is_bounds_query(input)) {
+        int mins[2] = {ox, oy}, ext[2] = {w + 2, h + 2};
+        hb::propose_shape(input, mins, ext);
+        query = true;
+    }
+    if (hb::is_bounds_query(blur_y)) {
+        int mins[2] = {ox, oy}, ext[2] = {w, h};
+        hb::propose_shape(blur_y, mins, ext);
+        query = true;
+    }
+    if (query) return 0;
+
+    if ((r = hb::check_shape(input, kIn))) return r;
+    if ((r = hb::check_shape(blur_y, kOut))) return r;
+    if ((r = hb::check_covers(input, kIn, 0, ox, w + 2))) return r;
+    if ((r = hb::check_covers(input, kIn, 1, oy, h + 2))) return r;
+    if (w <= 0 || h <= 0) return 0;
+
+    void *din = nullptr, *dout = nullptr;
+    if ((r = hb::acquire_input(input, kIn, &din))) return r;
+    if ((r = hb::acquire_output(blur_y, kOut, &dout))) return r;
+
+    BlurArgs a;
+    const int64_t isy = input->dim[1].stride;
+    const int64_t origin = (int64_t)(ox - input->dim[0].min) + (int64_t)(oy - input->dim[1].min) * isy;
+    a.in = (const uint16_t *)din + origin;
+    a.out = (uint16_t *)dout;
+    a.in_stride_y = isy;
+    a.out_stride_y = blur_y->dim[1].stride;
+    a.w = w;
+    a.h = h;
+    // allocation span of the input relative to a.in (dim0 stride is 1; dim1 stride may be negative)
+    int64_t reach1 = (int64_t)(input->dim[1].extent - 1) * isy;
+    int64_t lo = reach1 < 0 ? reach1 : 0, hi = (reach1 > 0 ? reach1 : 0) + input->dim[0].extent - 1;
+    a.in_lo = lo - origin;
+    a.in_hi = hi - origin;
+
+    // Enough warps to cover 148 SMs a few times over, but strips tall enough to amortise the
+    // two-row vertical apron.
+    int strips_x = (w + kStripW - 1) / kStripW;
+    int rows = 32;
+    while (rows > 4 && (int64_t)strips_x * ((h + rows - 1) / rows) < 148 * 8) rows >>= 1;
+    a.rows_per_warp = rows;
+    int warps_y = (h + rows - 1) / rows;
+    dim3 grid(strips_x, (warps_y + kWarpsPerBlock - 1) / kWarpsPerBlock);
+
+    cudaStream_t s = hb::stream();
+    {
+        hb::CallTimer timer(s);
+        HB_LAUNCH("blur3x3_u16", blur3x3_u16_kernel, grid, 32 * kWarpsPerBlock, 0, s, a);
+    }
+    if ((r = hb::check_cuda(cudaGetLastError(), "halide_blur launch", halide_error_code_device_run_failed))) return r;
+    hb::mark_output_written(blur_y);
+    return 0;
+}
+
+extern "C" int halide_blur_argv(void **args) {
+    return halide_blur((halide_buffer_t *)args[0], (halide_buffer_t *)args[1]);
+}
+
+extern "C" const halide_filter_metadata_t *halide_blur_metadata(void) {
+    return &kMeta;
+}

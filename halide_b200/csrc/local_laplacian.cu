@@ -1,0 +1,407 @@
+// local_laplacian.cu — local_laplacian(input, levels, alpha, beta, output) for sm_100a.
+//
+// Reference algorithm: apps/local_laplacian/local_laplacian_generator.cpp:19-87 (pipeline),
+// :266-273 (downsample 1-3-3-1, y then x), :276-282 (bilinear upsample); op order per
+// SURVEY.md Appendix B; parity target = oracle/oracle_local_laplacian.cpp, bit-exact on uint16.
+//
+// Data layout in HBM (all f32, callee-owned scratch):
+//   lut      [2*256*(levels-1)+1]            remap(i), i in [-256(levels-1), 256(levels-1)]
+//   gp[j]    [sy_j][gpitch_j][K]  j=1..J-1   gPyramid[j], the K=levels planes interleaved per
+//                                            pixel (K=8 -> one 32-byte sector per pixel, so the
+//                                            data-dependent (li, li+1) plane pick costs one sector)
+//   ing[j]   [sy_j][gpitch_j]     j=1..J-1   inGPyramid[j]
+//   outg[j]  [oy_j][opitch_j]     j=1..J-1   outGPyramid[j]
+// gray / gPyramid[0] / lPyramid / outLPyramid / outGPyramid[0] are never materialised: they are
+// recomputed from the uint16 input where needed (8 f32 planes at full resolution would be
+// 32 B/px of traffic against 12 B/px of compulsory I/O).
+#include "hb_common.h"
+#include "hl_math.cuh"
+#include "ll_geom.h"
+
+namespace {
+
+using ll::Span;
+
+struct LLFrame {
+    const uint16_t *in;  // element at the input mins
+    int64_t in_sy, in_sc;
+    int in_x0, in_y0, in_c0, in_w, in_h, in_c;
+    uint16_t *out;  // element at the output mins
+    int64_t out_sy, out_sc;
+    int out_x0, out_y0, out_c0, W, H, C;
+    int levels;
+    float beta, flm1, inv_lm1;
+    const float *lut;
+    int lut_half;
+};
+
+struct LevelBuf {
+    float *gp;    // [sy][gpitch][K]
+    float *ing;   // [sy][gpitch]
+    float *outg;  // [oy][opitch]
+    Span sx, sy, ox, oy;
+    int gpitch, opitch;
+};
+
+// ---- level-0 quantities recomputed from the input ---------------------------------------------
+__device__ __forceinline__ float gray_at(const LLFrame &f, int x, int y) {
+    // floating(x,y,c) = clamped(x,y,c) / 65535.0f; gray = 0.299 r + 0.587 g + 0.114 b (generator :32-36)
+    int cx = hl::clampi(x, f.in_x0, f.in_x0 + f.in_w - 1) - f.in_x0;
+    int cy = hl::clampi(y, f.in_y0, f.in_y0 + f.in_h - 1) - f.in_y0;
+    const uint16_t *p = f.in + (int64_t)cy * f.in_sy + cx;
+    int c0 = hl::clampi(0, f.in_c0, f.in_c0 + f.in_c - 1) - f.in_c0;
+    int c1 = hl::clampi(1, f.in_c0, f.in_c0 + f.in_c - 1) - f.in_c0;
+    int c2 = hl::clampi(2, f.in_c0, f.in_c0 + f.in_c - 1) - f.in_c0;
+    float f0 = __fmul_rn((float)__ldg(p + c0 * f.in_sc), hl::kInv65535);
+    float f1 = __fmul_rn((float)__ldg(p + c1 * f.in_sc), hl::kInv65535);
+    float f2 = __fmul_rn((float)__ldg(p + c2 * f.in_sc), hl::kInv65535);
+    return __fadd_rn(__fadd_rn(__fmul_rn(0.299f, f0), __fmul_rn(0.587f, f1)), __fmul_rn(0.114f, f2));
+}
+
+__device__ __forceinline__ int lut_index(const LLFrame &f, float g) {
+    // idx = clamp(int(gray * (levels-1) * 256), 0, (levels-1)*256) (generator :42-43)
+    int idx = (int)__fmul_rn(__fmul_rn(g, f.flm1), 256.0f);
+    return hl::clampi(idx, 0, (f.levels - 1) * 256);
+}
+
+__device__ __forceinline__ float gp0_at(const LLFrame &f, float g, int idx, int k) {
+    // gPyramid[0](x,y,k) = beta*(gray - level) + level + remap(idx - 256k) (generator :41,44)
+    float level = __fmul_rn((float)k, f.inv_lm1);
+    float r = __ldg(f.lut + (idx - 256 * k + f.lut_half));
+    return __fadd_rn(__fadd_rn(__fmul_rn(f.beta, __fsub_rn(g, level)), level), r);
+}
+
+__device__ __forceinline__ float down4(float a, float b, float c, float d) {
+    // (f(-1) + 3*(f(0)+f(1)) + f(2)) / 8  (generator :270-271; /8.0f folds to *0.125f)
+    return __fmul_rn(__fadd_rn(__fadd_rn(a, __fmul_rn(3.0f, __fadd_rn(b, c))), d), 0.125f);
+}
+
+// ---- K0: remap LUT ----------------------------------------------------------------------------
+__global__ void ll_lut_kernel(float *lut, int lut_half, float alpha) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > 2 * lut_half) return;
+    // remap(x) = alpha * fx * exp(-fx*fx/2), fx = x / 256 (generator :24-25)
+    float fx = __fmul_rn((float)(t - lut_half), 0.00390625f);
+    float e = hl::halide_exp(__fmul_rn(__fmul_rn(__fsub_rn(0.0f, fx), fx), 0.5f));
+    lut[t] = __fmul_rn(__fmul_rn(alpha, fx), e);
+}
+
+// ---- K1 (v0): level 1 from the input ------------------------------------------------------------
+__global__ void ll_level1_naive_kernel(LLFrame f, LevelBuf L1) {
+    int tx = blockIdx.x * blockDim.x + threadIdx.x;
+    int ty = blockIdx.y * blockDim.y + threadIdx.y;
+    if (tx >= L1.sx.n() || ty >= L1.sy.n()) return;
+    int x = L1.sx.lo + tx, y = L1.sy.lo + ty;
+    float g[4][4];
+    int idx[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            g[r][i] = gray_at(f, 2 * x - 1 + i, 2 * y - 1 + r);
+            idx[r][i] = lut_index(f, g[r][i]);
+        }
+    }
+    float dy[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) dy[i] = down4(g[0][i], g[1][i], g[2][i], g[3][i]);
+    size_t pix = (size_t)ty * L1.gpitch + tx;
+    L1.ing[pix] = down4(dy[0], dy[1], dy[2], dy[3]);
+    for (int k = 0; k < f.levels; k++) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            dy[i] = down4(gp0_at(f, g[0][i], idx[0][i], k), gp0_at(f, g[1][i], idx[1][i], k),
+                          gp0_at(f, g[2][i], idx[2][i], k), gp0_at(f, g[3][i], idx[3][i], k));
+        }
+        L1.gp[pix * f.levels + k] = down4(dy[0], dy[1], dy[2], dy[3]);
+    }
+}
+
+// ---- K2 (v0): level j -> j+1 --------------------------------------------------------------------
+__global__ void ll_down_naive_kernel(LevelBuf src, LevelBuf dst, int K) {
+    int tx = blockIdx.x * blockDim.x + threadIdx.x;
+    int ty = blockIdx.y * blockDim.y + threadIdx.y;
+    if (tx >= dst.sx.n() || ty >= dst.sy.n()) return;
+    int x = dst.sx.lo + tx, y = dst.sy.lo + ty;
+    int cx[4], cy[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        cx[i] = hl::clampi(2 * x - 1 + i, src.sx.lo, src.sx.hi) - src.sx.lo;
+        cy[i] = hl::clampi(2 * y - 1 + i, src.sy.lo, src.sy.hi) - src.sy.lo;
+    }
+    size_t pix = (size_t)ty * dst.gpitch + tx;
+    for (int k = -1; k < K; k++) {
+        float dy[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            float v[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                size_t sp = (size_t)cy[r] * src.gpitch + cx[i];
+                v[r] = k < 0 ? src.ing[sp] : src.gp[sp * K + k];
+            }
+            dy[i] = down4(v[0], v[1], v[2], v[3]);
+        }
+        float o = down4(dy[0], dy[1], dy[2], dy[3]);
+        if (k < 0) dst.ing[pix] = o;
+        else dst.gp[pix * K + k] = o;
+    }
+}
+
+// ---- upsample helpers ---------------------------------------------------------------------------
+struct UpTaps {
+    int xa, xb, ya, yb;  // (x+1)/2, (x-1)/2, (y+1)/2, (y-1)/2 with floor division (generator :279-280)
+    float wx, wy;        // ((x%2)*2+1)/4
+};
+__device__ __forceinline__ UpTaps up_taps(int x, int y) {
+    UpTaps t;
+    t.xa = (x + 1) >> 1; t.xb = (x - 1) >> 1;
+    t.ya = (y + 1) >> 1; t.yb = (y - 1) >> 1;
+    t.wx = __fmul_rn((float)((x & 1) * 2 + 1), 0.25f);
+    t.wy = __fmul_rn((float)((y & 1) * 2 + 1), 0.25f);
+    return t;
+}
+__device__ __forceinline__ float up_combine(float faa, float fba, float fab, float fbb, float wx, float wy) {
+    // upx(x, ya) = lerp(f(xa,ya), f(xb,ya), wx); upy = lerp(upx(x,ya), upx(x,yb), wy)
+    float ua = hl::lerpf(faa, fba, wx);
+    float ub = hl::lerpf(fab, fbb, wx);
+    return hl::lerpf(ua, ub, wy);
+}
+
+// ---- K3 (v0): outGPyramid[j] for 1 <= j <= J-1 -----------------------------------------------------
+__global__ void ll_up_naive_kernel(LevelBuf cur, LevelBuf coarse, int K, float flm1, int levels, int is_top) {
+    int tx = blockIdx.x * blockDim.x + threadIdx.x;
+    int ty = blockIdx.y * blockDim.y + threadIdx.y;
+    if (tx >= cur.ox.n() || ty >= cur.oy.n()) return;
+    int x = cur.ox.lo + tx, y = cur.oy.lo + ty;
+    int sx = hl::clampi(x, cur.sx.lo, cur.sx.hi) - cur.sx.lo;
+    int sy = hl::clampi(y, cur.sy.lo, cur.sy.hi) - cur.sy.lo;
+    size_t sp = (size_t)sy * cur.gpitch + sx;
+    // split inGPyramid[j] into integer and fractional level (generator :67-69)
+    float level = __fmul_rn(cur.ing[sp], flm1);
+    int li = hl::clampi((int)level, 0, levels - 2);
+    float lf = __fsub_rn(level, (float)li);
+    float l0 = cur.gp[sp * K + li], l1 = cur.gp[sp * K + li + 1];
+    float o;
+    if (is_top) {
+        o = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, lf), l0), __fmul_rn(lf, l1));
+    } else {
+        UpTaps t = up_taps(x, y);
+        int xa = hl::clampi(t.xa, coarse.sx.lo, coarse.sx.hi) - coarse.sx.lo;
+        int xb = hl::clampi(t.xb, coarse.sx.lo, coarse.sx.hi) - coarse.sx.lo;
+        int ya = hl::clampi(t.ya, coarse.sy.lo, coarse.sy.hi) - coarse.sy.lo;
+        int yb = hl::clampi(t.yb, coarse.sy.lo, coarse.sy.hi) - coarse.sy.lo;
+        const float *paa = coarse.gp + ((size_t)ya * coarse.gpitch + xa) * K;
+        const float *pba = coarse.gp + ((size_t)ya * coarse.gpitch + xb) * K;
+        const float *pab = coarse.gp + ((size_t)yb * coarse.gpitch + xa) * K;
+        const float *pbb = coarse.gp + ((size_t)yb * coarse.gpitch + xb) * K;
+        // lPyramid[j] = gPyramid[j] - upsample(gPyramid[j+1]) (generator :53)
+        l0 = __fsub_rn(l0, up_combine(paa[li], pba[li], pab[li], pbb[li], t.wx, t.wy));
+        l1 = __fsub_rn(l1, up_combine(paa[li + 1], pba[li + 1], pab[li + 1], pbb[li + 1], t.wx, t.wy));
+        float outl = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, lf), l0), __fmul_rn(lf, l1));
+        // outGPyramid[j] = upsample(outGPyramid[j+1]) + outLPyramid[j] (generator :78)
+        int oxa = t.xa - coarse.ox.lo, oxb = t.xb - coarse.ox.lo, oya = t.ya - coarse.oy.lo, oyb = t.yb - coarse.oy.lo;
+        float u = up_combine(coarse.outg[(size_t)oya * coarse.opitch + oxa], coarse.outg[(size_t)oya * coarse.opitch + oxb],
+                             coarse.outg[(size_t)oyb * coarse.opitch + oxa], coarse.outg[(size_t)oyb * coarse.opitch + oxb],
+                             t.wx, t.wy);
+        o = __fadd_rn(u, outl);
+    }
+    cur.outg[(size_t)ty * cur.opitch + tx] = o;
+}
+
+// ---- K4 (v0): level 0 + colour + cast -----------------------------------------------------------
+__global__ void ll_final_naive_kernel(LLFrame f, LevelBuf L1, int has_coarse) {
+    int tx = blockIdx.x * blockDim.x + threadIdx.x;
+    int ty = blockIdx.y * blockDim.y + threadIdx.y;
+    if (tx >= f.W || ty >= f.H) return;
+    int x = f.out_x0 + tx, y = f.out_y0 + ty;
+    const int K = f.levels;
+    float g = gray_at(f, x, y);
+    int idx = lut_index(f, g);
+    float level = __fmul_rn(g, f.flm1);
+    int li = hl::clampi((int)level, 0, f.levels - 2);
+    float lf = __fsub_rn(level, (float)li);
+    float l0 = gp0_at(f, g, idx, li), l1 = gp0_at(f, g, idx, li + 1);
+    float og0;
+    if (has_coarse) {
+        UpTaps t = up_taps(x, y);
+        int xa = hl::clampi(t.xa, L1.sx.lo, L1.sx.hi) - L1.sx.lo;
+        int xb = hl::clampi(t.xb, L1.sx.lo, L1.sx.hi) - L1.sx.lo;
+        int ya = hl::clampi(t.ya, L1.sy.lo, L1.sy.hi) - L1.sy.lo;
+        int yb = hl::clampi(t.yb, L1.sy.lo, L1.sy.hi) - L1.sy.lo;
+        const float *paa = L1.gp + ((size_t)ya * L1.gpitch + xa) * K;
+        const float *pba = L1.gp + ((size_t)ya * L1.gpitch + xb) * K;
+        const float *pab = L1.gp + ((size_t)yb * L1.gpitch + xa) * K;
+        const float *pbb = L1.gp + ((size_t)yb * L1.gpitch + xb) * K;
+        l0 = __fsub_rn(l0, up_combine(paa[li], pba[li], pab[li], pbb[li], t.wx, t.wy));
+        l1 = __fsub_rn(l1, up_combine(paa[li + 1], pba[li + 1], pab[li + 1], pbb[li + 1], t.wx, t.wy));
+        float outl = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, lf), l0), __fmul_rn(lf, l1));
+        int oxa = t.xa - L1.ox.lo, oxb = t.xb - L1.ox.lo, oya = t.ya - L1.oy.lo, oyb = t.yb - L1.oy.lo;
+        float u = up_combine(L1.outg[(size_t)oya * L1.opitch + oxa], L1.outg[(size_t)oya * L1.opitch + oxb],
+                             L1.outg[(size_t)oyb * L1.opitch + oxa], L1.outg[(size_t)oyb * L1.opitch + oxb], t.wx, t.wy);
+        og0 = __fadd_rn(u, outl);
+    } else {
+        og0 = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, lf), l0), __fmul_rn(lf, l1));
+    }
+    // color = input * (outG0 + eps) / (gray + eps); output = u16(clamp(color, 0, 65535)) (generator :82-87)
+    const float eps = 0.01f;
+    float num = __fadd_rn(og0, eps), den = __fadd_rn(g, eps);
+    const uint16_t *ip = f.in + (int64_t)(y - f.in_y0) * f.in_sy + (x - f.in_x0);
+    uint16_t *op = f.out + (int64_t)ty * f.out_sy + tx;
+    for (int c = 0; c < f.C; c++) {
+        int ca = f.out_c0 + c;  // absolute channel; the unclamped input(x,y,c) is read here
+        float v = __fdiv_rn(__fmul_rn((float)ip[(int64_t)(ca - f.in_c0) * f.in_sc], num), den);
+        op[(int64_t)c * f.out_sc] = (uint16_t)hl::clampf(v, 0.0f, 65535.0f);
+    }
+}
+
+const hb::ArgSpec kIn = {"input", halide_type_uint, 16, 3, false};
+const hb::ArgSpec kOut = {"output", halide_type_uint, 16, 3, true};
+
+int64_t est_i[3][2] = {{0, 1536}, {0, 2560}, {0, 3}};
+const int64_t *const est_ptrs[6] = {&est_i[0][0], &est_i[0][1], &est_i[1][0], &est_i[1][1], &est_i[2][0], &est_i[2][1]};
+halide_scalar_value_t sv_levels, sv_alpha, sv_beta;
+struct InitScalars {
+    InitScalars() {
+        sv_levels.u.i64 = 0; sv_levels.u.i32 = 8;
+        sv_alpha.u.i64 = 0; sv_alpha.u.f32 = 1.0f;
+        sv_beta.u.i64 = 0; sv_beta.u.f32 = 1.0f;
+    }
+} init_scalars;
+// Argument records as the generator declares them (generator :12-16, estimates :92-99).
+const halide_filter_argument_t kArgs[5] = {
+    {"input", halide_argument_kind_input_buffer, 3, {halide_type_uint, 16, 0}, nullptr, nullptr, nullptr, nullptr, est_ptrs},
+    {"levels", halide_argument_kind_input_scalar, 0, {halide_type_int, 32, 0}, nullptr, nullptr, nullptr, &sv_levels, nullptr},
+    {"alpha", halide_argument_kind_input_scalar, 0, {halide_type_float, 32, 0}, nullptr, nullptr, nullptr, &sv_alpha, nullptr},
+    {"beta", halide_argument_kind_input_scalar, 0, {halide_type_float, 32, 0}, nullptr, nullptr, nullptr, &sv_beta, nullptr},
+    {"output", halide_argument_kind_output_buffer, 3, {halide_type_uint, 16, 0}, nullptr, nullptr, nullptr, nullptr, est_ptrs},
+};
+const halide_filter_metadata_t kMeta = {1, 5, kArgs, "x86-64-linux-cuda-cuda_capability_100-b200_native", "local_laplacian"};
+const halide_filter_metadata_t kMetaAuto = {1, 5, kArgs, "x86-64-linux-cuda-cuda_capability_100-b200_native",
+                                            "local_laplacian_auto_schedule"};
+
+int run_local_laplacian(halide_buffer_t *input, int levels, float alpha, float beta, halide_buffer_t *output) {
+    int r;
+    if ((r = hb::check_arg(input, kIn))) return r;
+    if ((r = hb::check_arg(output, kOut))) return r;
+
+    // Bounds query: the only access that bypasses repeat_edge is input(x,y,c) in `color`
+    // (generator :84), so the input must cover exactly the output region.
+    bool query = false;
+    {
+        int mins[3] = {output->dim[0].min, output->dim[1].min, output->dim[2].min};
+        int ext[3] = {output->dim[0].extent, output->dim[1].extent, output->dim[2].extent};
+        if (hb::is_bounds_query(input)) {
+            hb::propose_shape(input, mins, ext);
+            query = true;
+        }
+        if (hb::is_bounds_query(output)) {
+            hb::propose_shape(output, mins, ext);
+            query = true;
+        }
+    }
+    if (query) return 0;
+
+    if ((r = hb::check_shape(input, kIn))) return r;
+    if ((r = hb::check_shape(output, kOut))) return r;
+    for (int d = 0; d < 3; d++) {
+        if ((r = hb::check_covers(input, kIn, d, output->dim[d].min, output->dim[d].extent))) return r;
+    }
+    if (levels < 2 || levels > 32) {
+        // 1/(levels-1) (generator :41) is meaningless below 2; the reference does not check, we do.
+        return hb::fail(levels < 2 ? halide_error_code_param_too_small : halide_error_code_param_too_large,
+                        "Parameter levels is %d but must be in [2, 32]", levels);
+    }
+    const int W = output->dim[0].extent, H = output->dim[1].extent, C = output->dim[2].extent;
+    if (W <= 0 || H <= 0 || C <= 0) return 0;
+
+    void *din = nullptr, *dout = nullptr;
+    if ((r = hb::acquire_input(input, kIn, &din))) return r;
+    if ((r = hb::acquire_output(output, kOut, &dout))) return r;
+
+    const int J = ll::kMaxJ;
+    const int K = levels;
+    Span outx = {output->dim[0].min, output->dim[0].min + W - 1}, outy = {output->dim[1].min, output->dim[1].min + H - 1};
+    Span inx = {input->dim[0].min, input->dim[0].min + input->dim[0].extent - 1};
+    Span iny = {input->dim[1].min, input->dim[1].min + input->dim[1].extent - 1};
+    ll::Geom geom = ll::make_geom(outx, outy, inx, iny, J);
+
+    hb::Scratch scratch;
+    LLFrame f;
+    f.in = (const uint16_t *)din;
+    f.in_sy = input->dim[1].stride; f.in_sc = input->dim[2].stride;
+    f.in_x0 = input->dim[0].min; f.in_y0 = input->dim[1].min; f.in_c0 = input->dim[2].min;
+    f.in_w = input->dim[0].extent; f.in_h = input->dim[1].extent; f.in_c = input->dim[2].extent;
+    f.out = (uint16_t *)dout;
+    f.out_sy = output->dim[1].stride; f.out_sc = output->dim[2].stride;
+    f.out_x0 = output->dim[0].min; f.out_y0 = output->dim[1].min; f.out_c0 = output->dim[2].min;
+    f.W = W; f.H = H; f.C = C;
+    f.levels = levels;
+    f.beta = beta;
+    f.flm1 = (float)(levels - 1);
+    f.inv_lm1 = 1.0f / (float)(levels - 1);
+    f.lut_half = 256 * (levels - 1);
+    float *lut = scratch.get<float>(2 * f.lut_half + 1);
+    if (!lut) return hb::fail(halide_error_code_device_malloc_failed, "local_laplacian: scratch allocation failed");
+    f.lut = lut;
+
+    LevelBuf lb[ll::kMaxJ];
+    for (int j = 1; j < J; j++) {
+        const ll::Level &lv = geom.lv[j];
+        lb[j].sx = lv.sx; lb[j].sy = lv.sy; lb[j].ox = lv.ox; lb[j].oy = lv.oy;
+        lb[j].gpitch = lv.gpitch; lb[j].opitch = lv.opitch;
+        size_t gpix = (size_t)lv.sy.n() * lv.gpitch;
+        lb[j].gp = scratch.get<float>(gpix * K);
+        lb[j].ing = scratch.get<float>(gpix);
+        lb[j].outg = scratch.get<float>((size_t)lv.oy.n() * lv.opitch);
+        if (!lb[j].gp || !lb[j].ing || !lb[j].outg) {
+            return hb::fail(halide_error_code_device_malloc_failed, "local_laplacian: scratch allocation failed");
+        }
+    }
+
+    cudaStream_t s = hb::stream();
+    {
+        hb::CallTimer timer(s);
+        HB_LAUNCH("ll_lut", ll_lut_kernel, (2 * f.lut_half + 1 + 255) / 256, 256, 0, s, lut, f.lut_half, alpha);
+        dim3 blk(32, 8);
+        auto grid_for = [&](int w, int h) { return dim3((w + 31) / 32, (h + 7) / 8); };
+        if (J > 1) {
+            HB_LAUNCH("ll_level1", ll_level1_naive_kernel, grid_for(lb[1].sx.n(), lb[1].sy.n()), blk, 0, s, f, lb[1]);
+            for (int j = 2; j < J; j++) {
+                HB_LAUNCH("ll_down", ll_down_naive_kernel, grid_for(lb[j].sx.n(), lb[j].sy.n()), blk, 0, s, lb[j - 1], lb[j], K);
+            }
+            for (int j = J - 1; j >= 1; j--) {
+                HB_LAUNCH("ll_up", ll_up_naive_kernel, grid_for(lb[j].ox.n(), lb[j].oy.n()), blk, 0, s, lb[j],
+                          lb[j == J - 1 ? j : j + 1], K, f.flm1, levels, j == J - 1 ? 1 : 0);
+            }
+        }
+        HB_LAUNCH("ll_final", ll_final_naive_kernel, grid_for(W, H), blk, 0, s, f, lb[1], J > 1 ? 1 : 0);
+    }
+    if ((r = hb::check_cuda(cudaGetLastError(), "local_laplacian launch", halide_error_code_device_run_failed))) return r;
+    hb::mark_output_written(output);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int local_laplacian(halide_buffer_t *input, int32_t levels, float alpha, float beta, halide_buffer_t *output) {
+    return run_local_laplacian(input, levels, alpha, beta, output);
+}
+extern "C" int local_laplacian_argv(void **args) {
+    return run_local_laplacian((halide_buffer_t *)args[0], *(int32_t *)args[1], *(float *)args[2], *(float *)args[3],
+                               (halide_buffer_t *)args[4]);
+}
+extern "C" const halide_filter_metadata_t *local_laplacian_metadata(void) {
+    return &kMeta;
+}
+// The harness's second AOT variant (apps/local_laplacian/process.cpp:44-48): same implementation.
+extern "C" int local_laplacian_auto_schedule(halide_buffer_t *input, int32_t levels, float alpha, float beta,
+                                             halide_buffer_t *output) {
+    return run_local_laplacian(input, levels, alpha, beta, output);
+}
+extern "C" int local_laplacian_auto_schedule_argv(void **args) {
+    return local_laplacian_argv(args);
+}
+extern "C" const halide_filter_metadata_t *local_laplacian_auto_schedule_metadata(void) {
+    return &kMetaAuto;
+}

@@ -1,0 +1,27 @@
+/* local_laplacian.h — stands in for the header Halide's AOT compiler emits for this filter
+ * (src/CodeGen_C.cpp:1083-1108 argument order: generator inputs in declaration order, then outputs;
+ *  src/CodeGen_C.cpp:675-721 for the _argv and _metadata companions).
+ * Generator: /root/reference/apps/local_laplacian/local_laplacian_generator.cpp:12-16,287
+ * Returns 0 or a negative halide_error_code_t (include/halide_b200_runtime.h).
+ */
+#ifndef HALIDE_B200_LOCAL_LAPLACIAN_H
+#define HALIDE_B200_LOCAL_LAPLACIAN_H
+
+#include <stdint.h>
+
+struct halide_buffer_t;
+struct halide_filter_metadata_t;
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int local_laplacian(struct halide_buffer_t *input, int32_t levels, float alpha, float beta, struct halide_buffer_t *output);
+int local_laplacian_argv(void **args);
+const struct halide_filter_metadata_t *local_laplacian_metadata(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* HALIDE_B200_LOCAL_LAPLACIAN_H */

@@ -1,0 +1,107 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so) — TEST INFRASTRUCTURE ONLY.
+
+Importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs; never from halide_b200/ (the product has no CPU path).
+Arrays are numpy, indexed outermost-first ([c, y, x] / [y, x]) like halide_b200.buffer.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liboracle.so")
+_REF_BLUR = os.path.join(_HERE, "_ref", "libref_blur.so")
+
+
+class oracle_image_t(ctypes.Structure):
+    _fields_ = [("base", ctypes.c_void_p), ("min", ctypes.c_int32 * 4), ("extent", ctypes.c_int32 * 4),
+                ("stride", ctypes.c_int32 * 4)]
+
+
+def build():
+    subprocess.check_call(["make", "-C", _HERE, "-s"])
+
+
+def _load():
+    if not os.path.exists(_LIB):
+        build()
+    l = ctypes.CDLL(_LIB)
+    for name in ("oracle_halide_exp", "oracle_halide_log", "oracle_fast_exp"):
+        getattr(l, name).restype = ctypes.c_float
+        getattr(l, name).argtypes = [ctypes.c_float]
+    l.oracle_halide_pow.restype = ctypes.c_float
+    l.oracle_halide_pow.argtypes = [ctypes.c_float, ctypes.c_float]
+    l.oracle_ll_remap.restype = ctypes.c_float
+    l.oracle_ll_remap.argtypes = [ctypes.c_int, ctypes.c_float]
+    return l
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = _load()
+    return _lib
+
+
+def image(arr, mins=None):
+    """Describe a numpy array (outermost-first indexing) as an oracle_image_t."""
+    img = oracle_image_t()
+    img.base = arr.ctypes.data
+    nd = arr.ndim
+    for d in range(nd):
+        img.extent[d] = arr.shape[nd - 1 - d]
+        img.stride[d] = arr.strides[nd - 1 - d] // arr.itemsize
+        img.min[d] = 0 if mins is None else mins[d]
+    for d in range(nd, 4):
+        img.extent[d] = 1
+    img._keep = arr
+    return img
+
+
+def blur(inp, out_shape=None, in_mins=None, out_mins=None):
+    """inp: uint16 [h, w]; returns uint16 [h-2, w-2] unless out_shape/mins say otherwise."""
+    h, w = inp.shape
+    if out_shape is None:
+        out_shape = (h - 2, w - 2)
+    out = np.zeros(out_shape, np.uint16)
+    r = lib().oracle_blur(ctypes.byref(image(inp, in_mins)), ctypes.byref(image(out, out_mins)))
+    if r != 0:
+        raise RuntimeError(f"oracle_blur returned {r}")
+    return out
+
+
+def local_laplacian(inp, levels, alpha, beta, out_shape=None, in_mins=None, out_mins=None, pyramid_levels=8):
+    """inp: uint16 [c, h, w]; alpha is the value the filter receives (already / (levels-1))."""
+    if out_shape is None:
+        out_shape = inp.shape
+    out = np.zeros(out_shape, np.uint16)
+    r = lib().oracle_local_laplacian(ctypes.byref(image(inp, in_mins)), ctypes.c_int(levels), ctypes.c_float(alpha),
+                                     ctypes.c_float(beta), ctypes.byref(image(out, out_mins)),
+                                     ctypes.c_int(pyramid_levels))
+    if r != 0:
+        raise RuntimeError(f"oracle_local_laplacian returned {r}")
+    return out
+
+
+def num_threads():
+    return lib().oracle_num_threads()
+
+
+def ref_blur_available():
+    return os.path.exists(_REF_BLUR)
+
+
+def ref_blur(inp, fast=False):
+    """The REFERENCE's own C blur (apps/blur/test.cpp:18-33 / :35-132) via oracle/_ref.
+    inp: uint16 [h, w] -> uint16 [h-2, w-8] (the shapes test.cpp uses)."""
+    l = ctypes.CDLL(_REF_BLUR)
+    h, w = inp.shape
+    inp = np.ascontiguousarray(inp)
+    out = np.zeros((h - 2, w - 8), np.uint16)
+    l.ref_blur(inp.ctypes.data_as(ctypes.c_void_p), w, h, out.ctypes.data_as(ctypes.c_void_p), 1 if fast else 0)
+    return out

@@ -1,0 +1,109 @@
+"""CPU tests of the drop-in boundary: the library loads and exports every symbol include/*.h
+declares; struct layouts match the LP64 facts of src/runtime/HalideRuntime.h:1657-1737."""
+import ctypes
+import glob
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    syms = set()
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        text = open(h).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        text = re.sub(r"//[^\n]*", "", text)
+        for m in re.finditer(r"^[A-Za-z_][\w \*]*?\b(\w+)\s*\([^;{]*\)\s*;", text, flags=re.M):
+            name = m.group(1)
+            if name.startswith(("halide_", "local_laplacian", "bilateral_grid", "nl_means", "stencil_chain",
+                                "conv_layer", "camera_pipe")):
+                syms.add(name)
+    return sorted(syms)
+
+
+def test_library_exports_every_declared_symbol(hb):
+    l = hb.load_library()
+    declared = _declared_symbols()
+    assert "local_laplacian" in declared and "halide_blur" in declared and "halide_copy_to_host" in declared
+    missing = [s for s in declared if not hasattr(l, s)]
+    assert not missing, f"declared in include/*.h but not exported: {missing}"
+
+
+def test_struct_layout(hb):
+    from halide_b200.buffer import halide_buffer_t, halide_dimension_t
+    assert ctypes.sizeof(halide_buffer_t) == 56
+    offs = {f: getattr(halide_buffer_t, f).offset for f, _ in halide_buffer_t._fields_}
+    assert offs == {"device": 0, "device_interface": 8, "host": 16, "flags": 24, "type": 32, "dimensions": 36,
+                    "dim": 40, "padding": 48}
+    assert ctypes.sizeof(halide_dimension_t) == 16
+
+
+def test_metadata_and_target(hb):
+    l = hb.load_library()
+
+    class Meta(ctypes.Structure):
+        _fields_ = [("version", ctypes.c_int32), ("num_arguments", ctypes.c_int32), ("arguments", ctypes.c_void_p),
+                    ("target", ctypes.c_char_p), ("name", ctypes.c_char_p)]
+    l.local_laplacian_metadata.restype = ctypes.POINTER(Meta)
+    md = l.local_laplacian_metadata().contents
+    assert md.version == 1 and md.num_arguments == 5 and md.name == b"local_laplacian"
+    assert b"cuda" in md.target
+    l.halide_blur_metadata.restype = ctypes.POINTER(Meta)
+    assert l.halide_blur_metadata().contents.num_arguments == 2
+
+
+def test_validation_errors_without_gpu(hb):
+    """Argument checks run before any CUDA call, so they are testable on a CPU-only box
+    (codes pinned by test/generator/error_codes_aottest.cpp:38-135)."""
+    import numpy as np
+    from halide_b200 import HalideBuffer, HalideError, filters
+    img = np.zeros((3, 16, 16), np.uint16)
+    out = np.zeros((3, 16, 16), np.uint16)
+    bi, bo = HalideBuffer.from_numpy(img), HalideBuffer.from_numpy(out)
+    # wrong element type -> -3
+    bad = HalideBuffer.from_numpy(np.zeros((3, 16, 16), np.float32))
+    with pytest.raises(HalideError) as e:
+        filters.local_laplacian(bad, 8, 1 / 7, 1.0, bo)
+    assert e.value.code == -3
+    # wrong dimensionality -> -43
+    bad2 = HalideBuffer.from_numpy(np.zeros((16, 16), np.uint16))
+    with pytest.raises(HalideError) as e:
+        filters.local_laplacian(bad2, 8, 1 / 7, 1.0, bo)
+    assert e.value.code == -43
+    # null buffer -> -12
+    l = hb.load_library()
+    assert l.local_laplacian(None, 8, ctypes.c_float(0.1), ctypes.c_float(1.0), bo.ptr) == -12
+    # input smaller than the output region -> -4
+    small = HalideBuffer.from_numpy(np.zeros((1, 16, 16), np.uint16))
+    with pytest.raises(HalideError) as e:
+        filters.local_laplacian(small, 8, 1 / 7, 1.0, bo)
+    assert e.value.code == -4
+    # stride[0] != 1 -> -8
+    bi.dims[0].stride = 2
+    with pytest.raises(HalideError) as e:
+        filters.local_laplacian(bi, 8, 1 / 7, 1.0, bo)
+    assert e.value.code == -8
+    # blur: input must cover output + 2 -> -4
+    b_in = HalideBuffer.from_numpy(np.zeros((10, 10), np.uint16))
+    b_out = HalideBuffer.from_numpy(np.zeros((10, 10), np.uint16))
+    with pytest.raises(HalideError) as e:
+        filters.halide_blur(b_in, b_out)
+    assert e.value.code == -4
+
+
+def test_bounds_query_mode(hb):
+    """A buffer with null host and device turns the call into a bounds query
+    (HalideRuntime.h:1851-1853, src/AddImageChecks.cpp:477-496): shapes are written, nothing runs."""
+    import numpy as np
+    from halide_b200 import HalideBuffer, filters
+    out = HalideBuffer.from_numpy(np.zeros((20, 30), np.uint16), mins=(5, 7))
+    q = HalideBuffer.bounds_query(np.uint16, 2)
+    assert filters.halide_blur(q, out) == 0
+    assert q.shape() == [(5, 32, 1), (7, 22, 32)]
+    out3 = HalideBuffer.from_numpy(np.zeros((3, 20, 30), np.uint16))
+    q3 = HalideBuffer.bounds_query(np.uint16, 3)
+    assert filters.local_laplacian(q3, 8, 1 / 7, 1.0, out3) == 0
+    assert q3.shape() == [(0, 30, 1), (0, 20, 30), (0, 3, 600)]
