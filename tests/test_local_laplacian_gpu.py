@@ -82,5 +82,7 @@ def test_4k_tile_consistency(hb, oracle):
     m = 1024  # margin: level-7 taps reach < 2^8 * 3 px; the crop keeps the true frame edge on two sides
     tl = oracle.local_laplacian(np.ascontiguousarray(img[:, :m, :m]), 8, 1.0 / 7.0, 1.0)
     assert np.array_equal(got[:, :160, :160], tl[:, :160, :160])
-    br = oracle.local_laplacian(np.ascontiguousarray(img[:, h - m:, w - m:]), 8, 1.0 / 7.0, 1.0)
+    # pyramid coordinates are absolute (parity of x,y matters in down/upsample): keep the crop's mins
+    br = oracle.local_laplacian(np.ascontiguousarray(img[:, h - m:, w - m:]), 8, 1.0 / 7.0, 1.0,
+                                in_mins=(w - m, h - m, 0), out_mins=(w - m, h - m, 0))
     assert np.array_equal(got[:, h - 160:, w - 160:], br[:, m - 160:, m - 160:])
