@@ -177,10 +177,10 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import halide_b200
     from halide_b200 import HalideBuffer, filters
-    from halide_b200 import lib as hlib
+    import halide_b200.lib as hlib
 
     torch.cuda.set_device(local_rank)
-    halide_b200.lib.halide_b200_set_device(local_rank)
+    halide_b200.capi.halide_b200_set_device(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as td
@@ -219,7 +219,7 @@ def run_ours(args, rank, world, local_rank):
     for i in range(args.warmup):
         step(i)
     barrier()
-    n0 = halide_b200.lib.halide_b200_kernel_launch_count()
+    n0 = halide_b200.capi.halide_b200_kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
     e0.record()
@@ -228,7 +228,7 @@ def run_ours(args, rank, world, local_rank):
     e1.record()
     barrier()
     sampler.stop()
-    launches = halide_b200.lib.halide_b200_kernel_launch_count() - n0
+    launches = halide_b200.capi.halide_b200_kernel_launch_count() - n0
     ms_total = e0.elapsed_time(e1)
     if dist is not None:
         tt = torch.tensor([ms_total], device=dev)

@@ -7,5 +7,6 @@ binding the tests and ``bench.py`` use to call that C ABI; it contains no comput
 fallback: importing :mod:`halide_b200.lib` raises if the shared library has not been built.
 """
 from .buffer import HalideBuffer, halide_buffer_t, halide_dimension_t  # noqa: F401
-from .lib import lib, load_library, HalideError, capture_errors  # noqa: F401
+from .lib import lib as capi, load_library, HalideError, capture_errors  # noqa: F401
+from . import lib  # noqa: F401  (module: loader + profile helpers)
 from . import filters  # noqa: F401

@@ -1,0 +1,290 @@
+// bilateral_grid.cu — bilateral_grid(input, r_sigma, output) for sm_100a (s_sigma = 8).
+//
+// Reference algorithm: apps/bilateral_grid/bilateral_grid_generator.cpp:17-67
+//   histogram(x,y,zi,c) += mux(c,{val,1}) over the 8x8 pixels of cell (x,y) (offset -4), zi = int(val/r_sigma + 0.5)
+//   blurz/blurx/blury: unnormalised 1-4-6-4-1 along z, x, y
+//   output = trilinear slice of blury at (x/8, y/8, val/r_sigma), channel 0 / channel 1
+// Float pipeline: parity bar is 1e-4 relative against oracle/oracle_bilateral_grid.cpp, so sums
+// may be re-associated (all terms are non-negative: no cancellation).
+//
+// HBM-bound: 8 algorithmic B/px (4 in + 4 out).  Three kernels:
+//   bg_hist_blurz   reads the frame once with coalesced float4 loads; each lane scatters its 4
+//                   columns x 8 rows into lane-private shared-memory bins (no atomics, no
+//                   conflicts: bin-major layout), the two lanes of a cell then emit blurz.
+//   bg_blur_xy      blurx then blury fused: each thread owns one (cell column, z, channel) and walks
+//                   down the grid rows with a 5-row register window of blurx values.
+//   bg_slice        4 pixels per thread (float4 in / float4 out), 8 float2 grid gathers per pixel
+//                   served by L1/L2 (the grid is ~0.4 B/px).
+// Grid layout in HBM: [cell_y][cell_x][z][2] f32 — the (z, z+1) x (value, weight) quad a pixel
+// needs at one corner is 16 contiguous bytes.
+#include "hb_common.h"
+#include "hl_math.cuh"
+
+namespace {
+
+constexpr int S = 8;  // s_sigma GeneratorParam of the shipped app (generator :8)
+
+struct BGParams {
+    const float *in;  // element at input mins
+    int64_t in_sy;
+    int in_x0, in_y0, in_w, in_h;
+    float *out;  // element at output mins
+    int64_t out_sy;
+    int out_x0, out_y0, W, H;
+    float inv_r;
+    int zmax;      // largest histogram bin
+    int nz;        // blurred grid planes: z in [0, zmax+1]
+    int gx0, gy0;  // first grid cell stored (absolute cell coordinates)
+    int gw, gh;    // stored cells
+    float *grid_a, *grid_b;  // [gh][gw][nz][2]
+};
+
+// ---- K1: histogram + blurz --------------------------------------------------------------------------
+// One warp handles 16 horizontally adjacent cells (128 px): lane l covers columns 4l..4l+3 of the
+// strip for all 8 rows of the cell row.  Bins live in shared memory as [bin][channel][thread].
+__global__ void __launch_bounds__(128) bg_hist_blurz_kernel(BGParams p) {
+    extern __shared__ float s_bins[];  // (zmax+1) * 2 * 128
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nb = p.zmax + 1;
+    for (int b = 0; b < nb * 2; b++) s_bins[b * 128 + tid] = 0.f;
+    const int cell_row = blockIdx.y;                       // index into stored rows
+    const int cell_col0 = (blockIdx.x * 4 + warp) * 16;    // first stored cell column of this warp
+    const int gy = p.gy0 + cell_row;
+    const int px0 = (p.gx0 + cell_col0) * S - S / 2 + 4 * lane;  // absolute x of this lane's first pixel
+    const bool interior_x = (px0 >= p.in_x0) && (px0 + 3 <= p.in_x0 + p.in_w - 1);
+#pragma unroll
+    for (int ry = 0; ry < S; ry++) {
+        int y = hl::clampi(gy * S + ry - S / 2, p.in_y0, p.in_y0 + p.in_h - 1) - p.in_y0;
+        const float *row = p.in + (int64_t)y * p.in_sy;
+        float v[4];
+        if (interior_x && ((reinterpret_cast<uintptr_t>(row + (px0 - p.in_x0)) & 15) == 0)) {
+            float4 t = __ldg(reinterpret_cast<const float4 *>(row + (px0 - p.in_x0)));
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                int x = hl::clampi(px0 + i, p.in_x0, p.in_x0 + p.in_w - 1) - p.in_x0;
+                v[i] = __ldg(row + x);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            float val = hl::clampf(v[i], 0.0f, 1.0f);
+            int zi = (int)__fadd_rn(__fmul_rn(val, p.inv_r), 0.5f);
+            zi = min(zi, p.zmax);
+            s_bins[(zi * 2) * 128 + tid] += val;
+            s_bins[(zi * 2 + 1) * 128 + tid] += 1.0f;
+        }
+    }
+    __syncwarp();
+    // lanes 2c, 2c+1 hold the two halves of cell c: even lane emits channel 0, odd lane channel 1
+    const int cell = cell_col0 + (lane >> 1);
+    if (cell >= p.gw) return;
+    const int ch = lane & 1;
+    const int ta = tid & ~1, tb = ta + 1;
+    auto h = [&](int z) -> float {
+        if (z < 0 || z > p.zmax) return 0.f;
+        return s_bins[(z * 2 + ch) * 128 + ta] + s_bins[(z * 2 + ch) * 128 + tb];
+    };
+    float *g = p.grid_a + ((size_t)cell_row * p.gw + cell) * p.nz * 2 + ch;
+    float hm2 = 0.f, hm1 = 0.f, h0 = h(0), h1 = h(1), h2 = h(2);
+    for (int z = 0; z < p.nz; z++) {
+        // blurz = h(z-2) + 4 h(z-1) + 6 h(z) + 4 h(z+1) + h(z+2) (generator :33-37)
+        g[z * 2] = (((hm2 + hm1 * 4.0f) + h0 * 6.0f) + h1 * 4.0f) + h2;
+        hm2 = hm1; hm1 = h0; h0 = h1; h1 = h2; h2 = h(z + 3);
+    }
+}
+
+// ---- K2: blurx + blury on the grid -------------------------------------------------------------------
+// blury is only needed on the interior (stored region shrunk by 2 cells on every side); the result is
+// written over the same extent with the border cells left untouched (never read by the slice).
+__global__ void __launch_bounds__(256) bg_blur_xy_kernel(BGParams p, int rows_per_block) {
+    const int V = p.nz * 2;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;  // (cell_x - 2) * V + v
+    const int cx = t / V + 2;
+    if (cx >= p.gw - 2) return;
+    const int v = t - (cx - 2) * V;
+    const int y_begin = 2 + blockIdx.y * rows_per_block;
+    const int y_end = min(y_begin + rows_per_block, p.gh - 2);
+    if (y_begin >= y_end) return;
+    auto blurx_at = [&](int cy) -> float {
+        const float *r = p.grid_a + ((size_t)cy * p.gw + cx) * V + v;
+        return (((__ldg(r - 2 * V) + __ldg(r - V) * 4.0f) + __ldg(r) * 6.0f) + __ldg(r + V) * 4.0f) + __ldg(r + 2 * V);
+    };
+    float a = blurx_at(y_begin - 2), b = blurx_at(y_begin - 1), c = blurx_at(y_begin), d = blurx_at(y_begin + 1);
+    for (int cy = y_begin; cy < y_end; cy++) {
+        float e = blurx_at(cy + 2);
+        p.grid_b[((size_t)cy * p.gw + cx) * V + v] = (((a + b * 4.0f) + c * 6.0f) + d * 4.0f) + e;
+        a = b; b = c; c = d; d = e;
+    }
+}
+
+// ---- K3: trilinear slice + normalise -----------------------------------------------------------------
+__device__ __forceinline__ float bg_slice_px(const BGParams &p, float raw, int x, int y) {
+    float val = hl::clampf(raw, 0.0f, 1.0f);
+    float zv = __fmul_rn(val, p.inv_r);
+    int zi = (int)zv;
+    float zf = __fsub_rn(zv, (float)zi);
+    zi = min(zi, p.nz - 2);
+    float xf = __fmul_rn((float)(x & (S - 1)), 0.125f);
+    float yf = __fmul_rn((float)(y & (S - 1)), 0.125f);
+    int xi = (x >> 3) - p.gx0, yi = (y >> 3) - p.gy0;
+    const int V = p.nz * 2;
+    const float2 *c00 = reinterpret_cast<const float2 *>(p.grid_b + ((size_t)yi * p.gw + xi) * V) + zi;
+    const float2 *c01 = c00 + p.nz;                    // xi + 1
+    const float2 *c10 = c00 + (size_t)p.gw * p.nz;     // yi + 1
+    const float2 *c11 = c10 + p.nz;
+    float2 a0 = __ldg(c00), a1 = __ldg(c00 + 1), b0 = __ldg(c01), b1 = __ldg(c01 + 1);
+    float2 d0 = __ldg(c10), d1 = __ldg(c10 + 1), e0 = __ldg(c11), e1 = __ldg(c11 + 1);
+    // lerp nest x -> y -> z exactly as generator :59-64
+    float v0 = hl::lerpf(hl::lerpf(hl::lerpf(a0.x, b0.x, xf), hl::lerpf(d0.x, e0.x, xf), yf),
+                         hl::lerpf(hl::lerpf(a1.x, b1.x, xf), hl::lerpf(d1.x, e1.x, xf), yf), zf);
+    float v1 = hl::lerpf(hl::lerpf(hl::lerpf(a0.y, b0.y, xf), hl::lerpf(d0.y, e0.y, xf), yf),
+                         hl::lerpf(hl::lerpf(a1.y, b1.y, xf), hl::lerpf(d1.y, e1.y, xf), yf), zf);
+    return __fdiv_rn(v0, v1);
+}
+
+__global__ void __launch_bounds__(256) bg_slice_kernel(BGParams p) {
+    const int tx = blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 pixels
+    const int ty = blockIdx.y;
+    const int lx = tx * 4;
+    if (lx >= p.W) return;
+    const int y = p.out_y0 + ty, x = p.out_x0 + lx;
+    const float *ip = p.in + (int64_t)(y - p.in_y0) * p.in_sy + (x - p.in_x0);
+    float *op = p.out + (int64_t)ty * p.out_sy + lx;
+    const bool full = lx + 3 < p.W;
+    if (full && ((reinterpret_cast<uintptr_t>(ip) | reinterpret_cast<uintptr_t>(op)) & 15) == 0) {
+        float4 v = __ldg(reinterpret_cast<const float4 *>(ip));
+        float4 o;
+        o.x = bg_slice_px(p, v.x, x, y);
+        o.y = bg_slice_px(p, v.y, x + 1, y);
+        o.z = bg_slice_px(p, v.z, x + 2, y);
+        o.w = bg_slice_px(p, v.w, x + 3, y);
+        *reinterpret_cast<float4 *>(op) = o;
+    } else {
+        for (int i = 0; i < 4 && lx + i < p.W; i++) op[i] = bg_slice_px(p, __ldg(ip + i), x + i, y);
+    }
+}
+
+const hb::ArgSpec kIn = {"input", halide_type_float, 32, 2, false};
+const hb::ArgSpec kOut = {"bilateral_grid", halide_type_float, 32, 2, true};
+int64_t est_i[2][2] = {{0, 1536}, {0, 2560}};
+const int64_t *const est_ptrs[4] = {&est_i[0][0], &est_i[0][1], &est_i[1][0], &est_i[1][1]};
+halide_scalar_value_t sv_rsigma;
+struct InitScalars {
+    InitScalars() { sv_rsigma.u.i64 = 0; sv_rsigma.u.f32 = 0.1f; }
+} init_scalars;
+const halide_filter_argument_t kArgs[3] = {
+    {"input", halide_argument_kind_input_buffer, 2, {halide_type_float, 32, 0}, nullptr, nullptr, nullptr, nullptr, est_ptrs},
+    {"r_sigma", halide_argument_kind_input_scalar, 0, {halide_type_float, 32, 0}, nullptr, nullptr, nullptr, &sv_rsigma, nullptr},
+    {"bilateral_grid", halide_argument_kind_output_buffer, 2, {halide_type_float, 32, 0}, nullptr, nullptr, nullptr, nullptr, est_ptrs},
+};
+const halide_filter_metadata_t kMeta = {1, 3, kArgs, "x86-64-linux-cuda-cuda_capability_100-b200_native", "bilateral_grid"};
+const halide_filter_metadata_t kMetaAuto = {1, 3, kArgs, "x86-64-linux-cuda-cuda_capability_100-b200_native",
+                                            "bilateral_grid_auto_schedule"};
+
+inline int fdiv(int a, int b) {  // floor division, b > 0
+    int q = a / b;
+    return (a % b != 0 && a < 0) ? q - 1 : q;
+}
+
+int run_bilateral_grid(halide_buffer_t *input, float r_sigma, halide_buffer_t *output) {
+    int r;
+    if ((r = hb::check_arg(input, kIn))) return r;
+    if ((r = hb::check_arg(output, kOut))) return r;
+    bool query = false;
+    {
+        // the slice reads input(x,y) unclamped (generator :50): the input must cover the output region
+        int mins[2] = {output->dim[0].min, output->dim[1].min};
+        int ext[2] = {output->dim[0].extent, output->dim[1].extent};
+        if (hb::is_bounds_query(input)) { hb::propose_shape(input, mins, ext); query = true; }
+        if (hb::is_bounds_query(output)) { hb::propose_shape(output, mins, ext); query = true; }
+    }
+    if (query) return 0;
+    if ((r = hb::check_shape(input, kIn))) return r;
+    if ((r = hb::check_shape(output, kOut))) return r;
+    for (int d = 0; d < 2; d++) {
+        if ((r = hb::check_covers(input, kIn, d, output->dim[d].min, output->dim[d].extent))) return r;
+    }
+    const int W = output->dim[0].extent, H = output->dim[1].extent;
+    if (W <= 0 || H <= 0) return 0;
+    if (!(r_sigma > 0.0f)) {
+        return hb::fail(halide_error_code_param_too_small, "Parameter r_sigma is %g but must be positive", (double)r_sigma);
+    }
+    BGParams p;
+    p.inv_r = 1.0f / r_sigma;
+    p.zmax = (int)(1.0f * p.inv_r + 0.5f);
+    p.nz = p.zmax + 2;
+    const size_t bins_bytes = (size_t)(p.zmax + 1) * 2 * 128 * sizeof(float);
+    if (bins_bytes > 200 * 1024) {
+        return hb::fail(halide_error_code_param_too_small,
+                        "Parameter r_sigma is %g: more than %d intensity bins are not supported by this build",
+                        (double)r_sigma, (int)(200 * 1024 / (2 * 128 * sizeof(float))));
+    }
+    void *din = nullptr, *dout = nullptr;
+    if ((r = hb::acquire_input(input, kIn, &din))) return r;
+    if ((r = hb::acquire_output(output, kOut, &dout))) return r;
+
+    const int ox = output->dim[0].min, oy = output->dim[1].min;
+    p.in = (const float *)din;
+    p.in_sy = input->dim[1].stride;
+    p.in_x0 = input->dim[0].min; p.in_y0 = input->dim[1].min;
+    p.in_w = input->dim[0].extent; p.in_h = input->dim[1].extent;
+    p.out = (float *)dout;
+    p.out_sy = output->dim[1].stride;
+    p.out_x0 = ox; p.out_y0 = oy; p.W = W; p.H = H;
+    // cells the slice touches are xi..xi+1; blury/blurx add 2 cells on every side
+    p.gx0 = fdiv(ox, S) - 2;
+    p.gy0 = fdiv(oy, S) - 2;
+    p.gw = fdiv(ox + W - 1, S) + 1 + 2 - p.gx0 + 1;
+    p.gh = fdiv(oy + H - 1, S) + 1 + 2 - p.gy0 + 1;
+    hb::Scratch scratch;
+    const size_t gelems = (size_t)p.gw * p.gh * p.nz * 2;
+    p.grid_a = scratch.get<float>(gelems);
+    p.grid_b = scratch.get<float>(gelems);
+    if (!p.grid_a || !p.grid_b) return hb::fail(halide_error_code_device_malloc_failed, "bilateral_grid: scratch allocation failed");
+
+    cudaStream_t s = hb::stream();
+    {
+        hb::CallTimer timer(s);
+        static bool attr_set = false;
+        if (bins_bytes > 48 * 1024 && !attr_set) {
+            cudaFuncSetAttribute(bg_hist_blurz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_set = true;
+        }
+        dim3 g1((p.gw + 63) / 64, p.gh);
+        HB_LAUNCH("bg_hist_blurz", bg_hist_blurz_kernel, g1, 128, bins_bytes, s, p);
+        const int V = p.nz * 2;
+        const int cols = (p.gw - 4) * V;
+        int rows = 16;
+        while (rows > 2 && (int64_t)((cols + 255) / 256) * ((p.gh - 4 + rows - 1) / rows) < 148 * 4) rows >>= 1;
+        dim3 g2((cols + 255) / 256, (p.gh - 4 + rows - 1) / rows);
+        HB_LAUNCH("bg_blur_xy", bg_blur_xy_kernel, g2, 256, 0, s, p, rows);
+        dim3 g3(((W + 3) / 4 + 255) / 256, H);
+        HB_LAUNCH("bg_slice", bg_slice_kernel, g3, 256, 0, s, p);
+    }
+    if ((r = hb::check_cuda(cudaGetLastError(), "bilateral_grid launch", halide_error_code_device_run_failed))) return r;
+    hb::mark_output_written(output);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int bilateral_grid(halide_buffer_t *input, float r_sigma, halide_buffer_t *output) {
+    return run_bilateral_grid(input, r_sigma, output);
+}
+extern "C" int bilateral_grid_argv(void **args) {
+    return run_bilateral_grid((halide_buffer_t *)args[0], *(float *)args[1], (halide_buffer_t *)args[2]);
+}
+extern "C" const halide_filter_metadata_t *bilateral_grid_metadata(void) {
+    return &kMeta;
+}
+extern "C" int bilateral_grid_auto_schedule(halide_buffer_t *input, float r_sigma, halide_buffer_t *output) {
+    return run_bilateral_grid(input, r_sigma, output);
+}
+extern "C" int bilateral_grid_auto_schedule_argv(void **args) {
+    return bilateral_grid_argv(args);
+}
+extern "C" const halide_filter_metadata_t *bilateral_grid_auto_schedule_metadata(void) {
+    return &kMetaAuto;
+}

@@ -148,6 +148,107 @@ __global__ void ll_down_naive_kernel(LevelBuf src, LevelBuf dst, int K) {
     }
 }
 
+// ---- K1/K2 (fast path, K == 8): warp-strip downsample ----------------------------------------------
+// One warp owns 15 destination columns x R destination rows.  Lane l holds source column
+// 2*X1-1+l for all K+1 channels (K gPyramid planes + the inGPyramid plane), walks down the source
+// rows keeping a 4-row window in registers (each source row is produced exactly once per strip;
+// 2 of 2R+2 rows are apron), applies the 1-3-3-1 filter in y, then obtains its three right-hand
+// neighbours by shuffle for the filter in x.  Even lanes 0..28 store one 32-byte pixel each.
+// FROM_INPUT: the source rows are gPyramid[0]/gray recomputed from the uint16 frame with the remap
+// LUT staged in shared memory (level 0 is never materialised).
+constexpr int kStripCols = 15;
+
+template<int K, bool FROM_INPUT>
+__global__ void __launch_bounds__(128) ll_down_strip_kernel(LLFrame f, LevelBuf src, LevelBuf dst, int rows_per_warp) {
+    extern __shared__ float s_lut[];
+    if (FROM_INPUT) {
+        for (int i = threadIdx.x; i <= 2 * f.lut_half; i += blockDim.x) s_lut[i] = f.lut[i];
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int X1 = dst.sx.lo + (blockIdx.x * 4 + warp) * kStripCols;
+    if (X1 > dst.sx.hi) return;
+    const int Y1 = dst.sy.lo + blockIdx.y * rows_per_warp;
+    const int Y1e = min(Y1 + rows_per_warp, dst.sy.hi + 1);
+    const int cs = 2 * X1 - 1 + lane;
+
+    // column-dependent addressing, hoisted out of the row loop
+    const uint16_t *in0 = nullptr, *in1 = nullptr, *in2 = nullptr;
+    const float4 *gcol = nullptr;
+    const float *icol = nullptr;
+    if (FROM_INPUT) {
+        int cx = hl::clampi(cs, f.in_x0, f.in_x0 + f.in_w - 1) - f.in_x0;
+        int c0 = hl::clampi(0, f.in_c0, f.in_c0 + f.in_c - 1) - f.in_c0;
+        int c1 = hl::clampi(1, f.in_c0, f.in_c0 + f.in_c - 1) - f.in_c0;
+        int c2 = hl::clampi(2, f.in_c0, f.in_c0 + f.in_c - 1) - f.in_c0;
+        in0 = f.in + cx + c0 * f.in_sc;
+        in1 = f.in + cx + c1 * f.in_sc;
+        in2 = f.in + cx + c2 * f.in_sc;
+    } else {
+        int cx = hl::clampi(cs, src.sx.lo, src.sx.hi) - src.sx.lo;
+        gcol = reinterpret_cast<const float4 *>(src.gp) + (size_t)cx * (K / 4);
+        icol = src.ing + cx;
+    }
+    const float *lut_c = s_lut + f.lut_half;
+
+    auto load_row = [&](int ys, float (&v)[K + 1]) {
+        if (FROM_INPUT) {
+            int cy = hl::clampi(ys, f.in_y0, f.in_y0 + f.in_h - 1) - f.in_y0;
+            int64_t ro = (int64_t)cy * f.in_sy;
+            float f0 = __fmul_rn((float)__ldg(in0 + ro), hl::kInv65535);
+            float f1 = __fmul_rn((float)__ldg(in1 + ro), hl::kInv65535);
+            float f2 = __fmul_rn((float)__ldg(in2 + ro), hl::kInv65535);
+            float g = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, f0), __fmul_rn(0.587f, f1)), __fmul_rn(0.114f, f2));
+            int idx = lut_index(f, g);
+            float bg = 0.f;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                float level = __fmul_rn((float)k, f.inv_lm1);
+                bg = __fadd_rn(__fmul_rn(f.beta, __fsub_rn(g, level)), level);
+                v[k] = __fadd_rn(bg, lut_c[idx - 256 * k]);
+            }
+            v[K] = g;
+        } else {
+            int cy = hl::clampi(ys, src.sy.lo, src.sy.hi) - src.sy.lo;
+            size_t ro = (size_t)cy * src.gpitch;
+#pragma unroll
+            for (int q = 0; q < K / 4; q++) {
+                float4 t = __ldg(gcol + ro * (K / 4) + q);
+                v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+            }
+            v[K] = __ldg(icol + ro);
+        }
+    };
+
+    float ra[K + 1], rb[K + 1], rc[K + 1], rd[K + 1];
+    load_row(2 * Y1 - 1, ra);
+    load_row(2 * Y1, rb);
+    const bool writer = !(lane & 1) && lane < 2 * kStripCols && (X1 + (lane >> 1)) <= dst.sx.hi;
+    const size_t dcol = (size_t)(X1 + (lane >> 1) - dst.sx.lo);
+    for (int y1 = Y1; y1 < Y1e; y1++) {
+        load_row(2 * y1 + 1, rc);
+        load_row(2 * y1 + 2, rd);
+        float o[K + 1];
+#pragma unroll
+        for (int p = 0; p <= K; p++) {
+            float dy = down4(ra[p], rb[p], rc[p], rd[p]);
+            float d1 = __shfl_down_sync(0xffffffffu, dy, 1);
+            float d2 = __shfl_down_sync(0xffffffffu, dy, 2);
+            float d3 = __shfl_down_sync(0xffffffffu, dy, 3);
+            o[p] = down4(dy, d1, d2, d3);
+            ra[p] = rc[p];
+            rb[p] = rd[p];
+        }
+        if (writer) {
+            size_t pix = (size_t)(y1 - dst.sy.lo) * dst.gpitch + dcol;
+            float4 *dp = reinterpret_cast<float4 *>(dst.gp) + pix * (K / 4);
+#pragma unroll
+            for (int q = 0; q < K / 4; q++) dp[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+            dst.ing[pix] = o[K];
+        }
+    }
+}
+
 // ---- upsample helpers ---------------------------------------------------------------------------
 struct UpTaps {
     int xa, xb, ya, yb;  // (x+1)/2, (x-1)/2, (y+1)/2, (y-1)/2 with floor division (generator :279-280)
@@ -254,6 +355,8 @@ __global__ void ll_final_naive_kernel(LLFrame f, LevelBuf L1, int has_coarse) {
         op[(int64_t)c * f.out_sc] = (uint16_t)hl::clampf(v, 0.0f, 65535.0f);
     }
 }
+
+bool g_force_naive = false;  // tests flip this to cross-check the generic kernels (halide_b200_ll_force_generic)
 
 const hb::ArgSpec kIn = {"input", halide_type_uint, 16, 3, false};
 const hb::ArgSpec kOut = {"output", halide_type_uint, 16, 3, true};
@@ -366,9 +469,35 @@ int run_local_laplacian(halide_buffer_t *input, int levels, float alpha, float b
         dim3 blk(32, 8);
         auto grid_for = [&](int w, int h) { return dim3((w + 31) / 32, (h + 7) / 8); };
         if (J > 1) {
-            HB_LAUNCH("ll_level1", ll_level1_naive_kernel, grid_for(lb[1].sx.n(), lb[1].sy.n()), blk, 0, s, f, lb[1]);
+            const bool fast = (K == 8) && !g_force_naive;
+            auto strip_rows = [&](const LevelBuf &d) {
+                // tall strips amortise the 2-row apron; shrink them when the level is too small to fill 148 SMs
+                int rows = 16;
+                int sx = (d.sx.n() + kStripCols - 1) / kStripCols;
+                while (rows > 2 && (int64_t)((sx + 3) / 4) * ((d.sy.n() + rows - 1) / rows) < 148 * 4) rows >>= 1;
+                return rows;
+            };
+            auto strip_grid = [&](const LevelBuf &d, int rows) {
+                int sx = (d.sx.n() + kStripCols - 1) / kStripCols;
+                return dim3((sx + 3) / 4, (d.sy.n() + rows - 1) / rows);
+            };
+            if (fast) {
+                int rows = strip_rows(lb[1]);
+                size_t smem = (size_t)(2 * f.lut_half + 1) * sizeof(float);
+                HB_LAUNCH("ll_level1_strip", (ll_down_strip_kernel<8, true>), strip_grid(lb[1], rows), 128, smem, s, f, lb[1],
+                          lb[1], rows);
+            } else {
+                HB_LAUNCH("ll_level1", ll_level1_naive_kernel, grid_for(lb[1].sx.n(), lb[1].sy.n()), blk, 0, s, f, lb[1]);
+            }
             for (int j = 2; j < J; j++) {
-                HB_LAUNCH("ll_down", ll_down_naive_kernel, grid_for(lb[j].sx.n(), lb[j].sy.n()), blk, 0, s, lb[j - 1], lb[j], K);
+                if (fast) {
+                    int rows = strip_rows(lb[j]);
+                    HB_LAUNCH("ll_down_strip", (ll_down_strip_kernel<8, false>), strip_grid(lb[j], rows), 128, 0, s, f,
+                              lb[j - 1], lb[j], rows);
+                } else {
+                    HB_LAUNCH("ll_down", ll_down_naive_kernel, grid_for(lb[j].sx.n(), lb[j].sy.n()), blk, 0, s, lb[j - 1],
+                              lb[j], K);
+                }
             }
             for (int j = J - 1; j >= 1; j--) {
                 HB_LAUNCH("ll_up", ll_up_naive_kernel, grid_for(lb[j].ox.n(), lb[j].oy.n()), blk, 0, s, lb[j],
@@ -404,4 +533,9 @@ extern "C" int local_laplacian_auto_schedule_argv(void **args) {
 }
 extern "C" const halide_filter_metadata_t *local_laplacian_auto_schedule_metadata(void) {
     return &kMetaAuto;
+}
+
+// Test hook: route K == 8 calls through the generic (any `levels`) kernels so both paths stay covered.
+extern "C" void halide_b200_ll_force_generic(int enable) {
+    g_force_naive = enable != 0;
 }

@@ -20,3 +20,13 @@ def local_laplacian(input, levels, alpha, beta, output):
     (process.cpp:31) callers pass alpha already divided by (levels - 1)."""
     return check(lib.local_laplacian(input.ptr, ctypes.c_int32(levels), ctypes.c_float(alpha),
                                      ctypes.c_float(beta), output.ptr))
+
+
+def stencil_chain(input, output):
+    """apps/stencil_chain/stencil_chain_generator.cpp: 32 chained 5x5 uint16 stencils."""
+    return check(lib.stencil_chain(input.ptr, output.ptr))
+
+
+def bilateral_grid(input, r_sigma, output):
+    """apps/bilateral_grid/bilateral_grid_generator.cpp (s_sigma = 8), float32."""
+    return check(lib.bilateral_grid(input.ptr, ctypes.c_float(r_sigma), output.ptr))

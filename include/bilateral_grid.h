@@ -1,0 +1,27 @@
+/* bilateral_grid.h — stands in for the header Halide's AOT compiler emits for this filter
+ * (src/CodeGen_C.cpp:1083-1108 argument order: generator inputs in declaration order, then outputs;
+ *  src/CodeGen_C.cpp:675-721 for the _argv and _metadata companions).
+ * Generator: /root/reference/apps/bilateral_grid/bilateral_grid_generator.cpp:8-16,203
+ * Returns 0 or a negative halide_error_code_t (include/halide_b200_runtime.h).
+ */
+#ifndef HALIDE_B200_BILATERAL_GRID_H
+#define HALIDE_B200_BILATERAL_GRID_H
+
+#include <stdint.h>
+
+struct halide_buffer_t;
+struct halide_filter_metadata_t;
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int bilateral_grid(struct halide_buffer_t *input, float r_sigma, struct halide_buffer_t *bilateral_grid);
+int bilateral_grid_argv(void **args);
+const struct halide_filter_metadata_t *bilateral_grid_metadata(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* HALIDE_B200_BILATERAL_GRID_H */

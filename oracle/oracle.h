@@ -32,6 +32,15 @@ int oracle_blur(const oracle_image_t *in, const oracle_image_t *out);
 int oracle_local_laplacian(const oracle_image_t *in, int levels, float alpha, float beta,
                            const oracle_image_t *out, int pyramid_levels);
 
+// apps/bilateral_grid/bilateral_grid_generator.cpp:17-67 (s_sigma is the GeneratorParam, 8 in the app).
+int oracle_bilateral_grid(const oracle_image_t *in, float r_sigma, const oracle_image_t *out, int s_sigma);
+
+// apps/nl_means/nl_means_generator.cpp:24-63.  out has 3 channels.
+int oracle_nl_means(const oracle_image_t *in, int patch_size, int search_area, float sigma, const oracle_image_t *out);
+
+// apps/stencil_chain/stencil_chain_generator.cpp:16-34 (`stencils` is the GeneratorParam, 32 in the app).
+int oracle_stencil_chain(const oracle_image_t *in, const oracle_image_t *out, int stencils);
+
 // Primitive probes so the tests can pin the math helpers against known values.
 float oracle_halide_exp(float x);
 float oracle_halide_log(float x);

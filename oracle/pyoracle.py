@@ -105,3 +105,33 @@ def ref_blur(inp, fast=False):
     out = np.zeros((h - 2, w - 8), np.uint16)
     l.ref_blur(inp.ctypes.data_as(ctypes.c_void_p), w, h, out.ctypes.data_as(ctypes.c_void_p), 1 if fast else 0)
     return out
+
+
+def bilateral_grid(inp, r_sigma, out_shape=None, in_mins=None, out_mins=None, s_sigma=8):
+    """inp: float32 [h, w]."""
+    out = np.zeros(inp.shape if out_shape is None else out_shape, np.float32)
+    r = lib().oracle_bilateral_grid(ctypes.byref(image(inp, in_mins)), ctypes.c_float(r_sigma),
+                                    ctypes.byref(image(out, out_mins)), ctypes.c_int(s_sigma))
+    if r != 0:
+        raise RuntimeError(f"oracle_bilateral_grid returned {r}")
+    return out
+
+
+def nl_means(inp, patch_size, search_area, sigma, out_shape=None, in_mins=None, out_mins=None):
+    """inp: float32 [3, h, w]."""
+    out = np.zeros(inp.shape if out_shape is None else out_shape, np.float32)
+    r = lib().oracle_nl_means(ctypes.byref(image(inp, in_mins)), ctypes.c_int(patch_size), ctypes.c_int(search_area),
+                              ctypes.c_float(sigma), ctypes.byref(image(out, out_mins)))
+    if r != 0:
+        raise RuntimeError(f"oracle_nl_means returned {r}")
+    return out
+
+
+def stencil_chain(inp, out_shape=None, in_mins=None, out_mins=None, stencils=32):
+    """inp: uint16 [h, w]."""
+    out = np.zeros(inp.shape if out_shape is None else out_shape, np.uint16)
+    r = lib().oracle_stencil_chain(ctypes.byref(image(inp, in_mins)), ctypes.byref(image(out, out_mins)),
+                                   ctypes.c_int(stencils))
+    if r != 0:
+        raise RuntimeError(f"oracle_stencil_chain returned {r}")
+    return out

@@ -86,3 +86,18 @@ def test_4k_tile_consistency(hb, oracle):
     br = oracle.local_laplacian(np.ascontiguousarray(img[:, h - m:, w - m:]), 8, 1.0 / 7.0, 1.0,
                                 in_mins=(w - m, h - m, 0), out_mins=(w - m, h - m, 0))
     assert np.array_equal(got[:, h - 160:, w - 160:], br[:, m - 160:, m - 160:])
+
+
+def test_generic_kernels_agree_with_fast_path(hb, oracle):
+    """levels == 8 takes the warp-strip kernels; any other `levels` (and this hook) takes the generic
+    per-pixel kernels.  Both must equal the oracle."""
+    img = u16_frame((3, 131, 203), 31)
+    want = oracle.local_laplacian(img, 8, 1.0 / 7.0, 1.0)
+    l = hb.load_library()
+    try:
+        l.halide_b200_ll_force_generic(1)
+        got_generic = run_local_laplacian(hb, img, 8, 1.0 / 7.0, 1.0)
+    finally:
+        l.halide_b200_ll_force_generic(0)
+    got_fast = run_local_laplacian(hb, img, 8, 1.0 / 7.0, 1.0)
+    assert np.array_equal(got_generic, want) and np.array_equal(got_fast, want)
