@@ -30,3 +30,9 @@ def stencil_chain(input, output):
 def bilateral_grid(input, r_sigma, output):
     """apps/bilateral_grid/bilateral_grid_generator.cpp (s_sigma = 8), float32."""
     return check(lib.bilateral_grid(input.ptr, ctypes.c_float(r_sigma), output.ptr))
+
+
+def nl_means(input, patch_size, search_area, sigma, output):
+    """apps/nl_means/nl_means_generator.cpp, float32, output has exactly 3 channels."""
+    return check(lib.nl_means(input.ptr, ctypes.c_int32(patch_size), ctypes.c_int32(search_area),
+                              ctypes.c_float(sigma), output.ptr))

@@ -2,8 +2,8 @@
  * (src/CodeGen_C.cpp:1083-1108 argument order: generator inputs in declaration order, then outputs;
  *  src/CodeGen_C.cpp:675-721 for the _argv and _metadata companions).
  * Generator: /root/reference/apps/local_laplacian/local_laplacian_generator.cpp:12-16,287
- * `local_laplacian_auto_schedule` is the second AOT variant the harness links (apps/*/process.cpp builds without
- * -DNO_AUTO_SCHEDULE call it); here it is the same sm_100a implementation under the second name.
+ * `local_laplacian_auto_schedule` is the second AOT variant the harness links (the app harness, when built without
+ * -DNO_AUTO_SCHEDULE calls it); here it is the same sm_100a implementation under the second name.
  * Returns 0 or a negative halide_error_code_t (include/halide_b200_runtime.h).
  */
 #ifndef HALIDE_B200_LOCAL_LAPLACIAN_AUTO_SCHEDULE_H

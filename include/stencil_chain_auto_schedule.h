@@ -2,7 +2,7 @@
  * (src/CodeGen_C.cpp:1083-1108 argument order: generator inputs in declaration order, then outputs;
  *  src/CodeGen_C.cpp:675-721 for the _argv and _metadata companions).
  * Generator: /root/reference/apps/stencil_chain/stencil_chain_generator.cpp:7-14,150
- * `stencil_chain_auto_schedule` is the second AOT variant the harness links (apps/*/process.cpp built without
+ * `stencil_chain_auto_schedule` is the second AOT variant the harness links (the app harness, when built without
  * -DNO_AUTO_SCHEDULE calls it); here it is the same sm_100a implementation under the second name.
  * Returns 0 or a negative halide_error_code_t (include/halide_b200_runtime.h).
  */

@@ -95,7 +95,7 @@ def test_generic_kernels_agree_with_fast_path(hb, oracle):
     want = oracle.local_laplacian(img, 8, 1.0 / 7.0, 1.0)
     l = hb.load_library()
     try:
-        l.halide_b200_ll_force_generic(1)
+        l.halide_b200_ll_force_generic(7)
         got_generic = run_local_laplacian(hb, img, 8, 1.0 / 7.0, 1.0)
     finally:
         l.halide_b200_ll_force_generic(0)

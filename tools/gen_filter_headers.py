@@ -28,7 +28,7 @@ def emit(name):
         fn = name + suffix
         guard = "HALIDE_B200_" + fn.upper() + "_H"
         note = "" if not suffix else (
-            f" * `{fn}` is the second AOT variant the harness links (apps/*/process.cpp built without\n"
+            f" * `{fn}` is the second AOT variant the harness links (the app harness, when built without\n"
             f" * -DNO_AUTO_SCHEDULE calls it); here it is the same sm_100a implementation under the second name.\n")
         with open(os.path.join(ROOT, "include", fn + ".h"), "w") as f:
             f.write(f"""/* {fn}.h — stands in for the header Halide's AOT compiler emits for this filter
