@@ -1,0 +1,21 @@
+// hb_dist.h — halo-exchange primitive used by the row-sharded filters (implemented in hb_dist.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace hbdist {
+
+struct Msg {
+    void *ptr;     // device address
+    size_t bytes;
+    int peer;      // rank
+    bool send;     // true: ncclSend, false: ncclRecv
+};
+
+bool active();
+int rank();
+int size();
+// One ncclGroup of point-to-point messages enqueued on stream `s` (ordered with the kernels on it).
+int exchange(const Msg *msgs, int n, cudaStream_t s);
+
+}  // namespace hbdist

@@ -1,8 +1,7 @@
-// local_laplacian.cu — local_laplacian(input, levels, alpha, beta, output) for sm_100a.
-//
-// Reference algorithm: apps/local_laplacian/local_laplacian_generator.cpp:19-87 (pipeline),
-// :266-273 (downsample 1-3-3-1, y then x), :276-282 (bilinear upsample); op order per
-// SURVEY.md Appendix B; parity target = oracle/oracle_local_laplacian.cpp, bit-exact on uint16.
+// local_laplacian.cu — host side of local_laplacian(input, levels, alpha, beta, output) for sm_100a:
+// the C-ABI entry points (reference: apps/local_laplacian/local_laplacian_generator.cpp:12-16,287 and
+// the harness apps/local_laplacian/process.cpp:31), argument validation, pyramid geometry, scratch
+// allocation, the launch sequence, and the row-sharded multi-GPU variant.  Kernels: ll_kernels.cuh.
 //
 // Data layout in HBM (all f32, callee-owned scratch):
 //   lut      [2*256*(levels-1)+1]            remap(i), i in [-256(levels-1), 256(levels-1)]
@@ -14,570 +13,12 @@
 // gray / gPyramid[0] / lPyramid / outLPyramid / outGPyramid[0] are never materialised: they are
 // recomputed from the uint16 input where needed (8 f32 planes at full resolution would be
 // 32 B/px of traffic against 12 B/px of compulsory I/O).
-#include "hb_common.h"
-#include "hl_math.cuh"
-#include "ll_geom.h"
+#include "hb_dist.h"
+#include "ll_kernels.cuh"
 
 namespace {
 
-using ll::Span;
-
-struct LLFrame {
-    const uint16_t *in;  // element at the input mins
-    int64_t in_sy, in_sc;
-    int in_x0, in_y0, in_c0, in_w, in_h, in_c;
-    uint16_t *out;  // element at the output mins
-    int64_t out_sy, out_sc;
-    int out_x0, out_y0, out_c0, W, H, C;
-    int levels;
-    float beta, flm1, inv_lm1;
-    const float *lut;
-    int lut_half;
-};
-
-struct LevelBuf {
-    float *gp;    // [sy][gpitch][K]
-    float *ing;   // [sy][gpitch]
-    float *outg;  // [oy][opitch]
-    Span sx, sy, ox, oy;
-    int gpitch, opitch;
-};
-
-// ---- level-0 quantities recomputed from the input ---------------------------------------------
-__device__ __forceinline__ float gray_at(const LLFrame &f, int x, int y) {
-    // floating(x,y,c) = clamped(x,y,c) / 65535.0f; gray = 0.299 r + 0.587 g + 0.114 b (generator :32-36)
-    int cx = hl::clampi(x, f.in_x0, f.in_x0 + f.in_w - 1) - f.in_x0;
-    int cy = hl::clampi(y, f.in_y0, f.in_y0 + f.in_h - 1) - f.in_y0;
-    const uint16_t *p = f.in + (int64_t)cy * f.in_sy + cx;
-    int c0 = hl::clampi(0, f.in_c0, f.in_c0 + f.in_c - 1) - f.in_c0;
-    int c1 = hl::clampi(1, f.in_c0, f.in_c0 + f.in_c - 1) - f.in_c0;
-    int c2 = hl::clampi(2, f.in_c0, f.in_c0 + f.in_c - 1) - f.in_c0;
-    float f0 = __fmul_rn((float)__ldg(p + c0 * f.in_sc), hl::kInv65535);
-    float f1 = __fmul_rn((float)__ldg(p + c1 * f.in_sc), hl::kInv65535);
-    float f2 = __fmul_rn((float)__ldg(p + c2 * f.in_sc), hl::kInv65535);
-    return __fadd_rn(__fadd_rn(__fmul_rn(0.299f, f0), __fmul_rn(0.587f, f1)), __fmul_rn(0.114f, f2));
-}
-
-__device__ __forceinline__ int lut_index(const LLFrame &f, float g) {
-    // idx = clamp(int(gray * (levels-1) * 256), 0, (levels-1)*256) (generator :42-43)
-    int idx = (int)__fmul_rn(__fmul_rn(g, f.flm1), 256.0f);
-    return hl::clampi(idx, 0, (f.levels - 1) * 256);
-}
-
-__device__ __forceinline__ float gp0_at(const LLFrame &f, float g, int idx, int k) {
-    // gPyramid[0](x,y,k) = beta*(gray - level) + level + remap(idx - 256k) (generator :41,44)
-    float level = __fmul_rn((float)k, f.inv_lm1);
-    float r = __ldg(f.lut + (idx - 256 * k + f.lut_half));
-    return __fadd_rn(__fadd_rn(__fmul_rn(f.beta, __fsub_rn(g, level)), level), r);
-}
-
-__device__ __forceinline__ float down4(float a, float b, float c, float d) {
-    // (f(-1) + 3*(f(0)+f(1)) + f(2)) / 8  (generator :270-271; /8.0f folds to *0.125f)
-    return __fmul_rn(__fadd_rn(__fadd_rn(a, __fmul_rn(3.0f, __fadd_rn(b, c))), d), 0.125f);
-}
-
-// ---- K0: remap LUT ----------------------------------------------------------------------------
-__global__ void ll_lut_kernel(float *lut, int lut_half, float alpha) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t > 2 * lut_half) return;
-    // remap(x) = alpha * fx * exp(-fx*fx/2), fx = x / 256 (generator :24-25)
-    float fx = __fmul_rn((float)(t - lut_half), 0.00390625f);
-    float e = hl::halide_exp(__fmul_rn(__fmul_rn(__fsub_rn(0.0f, fx), fx), 0.5f));
-    lut[t] = __fmul_rn(__fmul_rn(alpha, fx), e);
-}
-
-// ---- K1 (v0): level 1 from the input ------------------------------------------------------------
-__global__ void ll_level1_naive_kernel(LLFrame f, LevelBuf L1) {
-    int tx = blockIdx.x * blockDim.x + threadIdx.x;
-    int ty = blockIdx.y * blockDim.y + threadIdx.y;
-    if (tx >= L1.sx.n() || ty >= L1.sy.n()) return;
-    int x = L1.sx.lo + tx, y = L1.sy.lo + ty;
-    float g[4][4];
-    int idx[4][4];
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            g[r][i] = gray_at(f, 2 * x - 1 + i, 2 * y - 1 + r);
-            idx[r][i] = lut_index(f, g[r][i]);
-        }
-    }
-    float dy[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) dy[i] = down4(g[0][i], g[1][i], g[2][i], g[3][i]);
-    size_t pix = (size_t)ty * L1.gpitch + tx;
-    L1.ing[pix] = down4(dy[0], dy[1], dy[2], dy[3]);
-    for (int k = 0; k < f.levels; k++) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            dy[i] = down4(gp0_at(f, g[0][i], idx[0][i], k), gp0_at(f, g[1][i], idx[1][i], k),
-                          gp0_at(f, g[2][i], idx[2][i], k), gp0_at(f, g[3][i], idx[3][i], k));
-        }
-        L1.gp[pix * f.levels + k] = down4(dy[0], dy[1], dy[2], dy[3]);
-    }
-}
-
-// ---- K2 (v0): level j -> j+1 --------------------------------------------------------------------
-__global__ void ll_down_naive_kernel(LevelBuf src, LevelBuf dst, int K) {
-    int tx = blockIdx.x * blockDim.x + threadIdx.x;
-    int ty = blockIdx.y * blockDim.y + threadIdx.y;
-    if (tx >= dst.sx.n() || ty >= dst.sy.n()) return;
-    int x = dst.sx.lo + tx, y = dst.sy.lo + ty;
-    int cx[4], cy[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        cx[i] = hl::clampi(2 * x - 1 + i, src.sx.lo, src.sx.hi) - src.sx.lo;
-        cy[i] = hl::clampi(2 * y - 1 + i, src.sy.lo, src.sy.hi) - src.sy.lo;
-    }
-    size_t pix = (size_t)ty * dst.gpitch + tx;
-    for (int k = -1; k < K; k++) {
-        float dy[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            float v[4];
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                size_t sp = (size_t)cy[r] * src.gpitch + cx[i];
-                v[r] = k < 0 ? src.ing[sp] : src.gp[sp * K + k];
-            }
-            dy[i] = down4(v[0], v[1], v[2], v[3]);
-        }
-        float o = down4(dy[0], dy[1], dy[2], dy[3]);
-        if (k < 0) dst.ing[pix] = o;
-        else dst.gp[pix * K + k] = o;
-    }
-}
-
-// ---- K1/K2 (fast path, K == 8): warp-strip downsample ----------------------------------------------
-// One warp owns 15 destination columns x R destination rows.  Lane l holds source column
-// 2*X1-1+l for all K+1 channels (K gPyramid planes + the inGPyramid plane), walks down the source
-// rows keeping a 4-row window in registers (each source row is produced exactly once per strip;
-// 2 of 2R+2 rows are apron), applies the 1-3-3-1 filter in y, then obtains its three right-hand
-// neighbours by shuffle for the filter in x.  Even lanes 0..28 store one 32-byte pixel each.
-// FROM_INPUT: the source rows are gPyramid[0]/gray recomputed from the uint16 frame with the remap
-// LUT staged in shared memory (level 0 is never materialised).
-constexpr int kStripCols = 15;
-
-template<int K, bool FROM_INPUT>
-__global__ void __launch_bounds__(128) ll_down_strip_kernel(LLFrame f, LevelBuf src, LevelBuf dst, int rows_per_warp) {
-    extern __shared__ float s_lut[];
-    if (FROM_INPUT) {
-        for (int i = threadIdx.x; i <= 2 * f.lut_half; i += blockDim.x) s_lut[i] = f.lut[i];
-        __syncthreads();
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int X1 = dst.sx.lo + (blockIdx.x * 4 + warp) * kStripCols;
-    if (X1 > dst.sx.hi) return;
-    const int Y1 = dst.sy.lo + blockIdx.y * rows_per_warp;
-    const int Y1e = min(Y1 + rows_per_warp, dst.sy.hi + 1);
-    const int cs = 2 * X1 - 1 + lane;
-
-    // column-dependent addressing, hoisted out of the row loop
-    const uint16_t *in0 = nullptr, *in1 = nullptr, *in2 = nullptr;
-    const float4 *gcol = nullptr;
-    const float *icol = nullptr;
-    if (FROM_INPUT) {
-        int cx = hl::clampi(cs, f.in_x0, f.in_x0 + f.in_w - 1) - f.in_x0;
-        int c0 = hl::clampi(0, f.in_c0, f.in_c0 + f.in_c - 1) - f.in_c0;
-        int c1 = hl::clampi(1, f.in_c0, f.in_c0 + f.in_c - 1) - f.in_c0;
-        int c2 = hl::clampi(2, f.in_c0, f.in_c0 + f.in_c - 1) - f.in_c0;
-        in0 = f.in + cx + c0 * f.in_sc;
-        in1 = f.in + cx + c1 * f.in_sc;
-        in2 = f.in + cx + c2 * f.in_sc;
-    } else {
-        int cx = hl::clampi(cs, src.sx.lo, src.sx.hi) - src.sx.lo;
-        gcol = reinterpret_cast<const float4 *>(src.gp) + (size_t)cx * (K / 4);
-        icol = src.ing + cx;
-    }
-    const float *lut_c = s_lut + f.lut_half;
-
-    // channels are carried as packed pairs (planes 2q, 2q+1) so the 1-3-3-1 filters and the gPyramid[0]
-    // evaluation issue as FADD2/FMUL2 (per-component round-to-nearest: same bits as the scalar ops);
-    // the inGPyramid plane rides alone in `s`.
-    struct Row {
-        float2 v[K / 2];
-        float s;
-    };
-    auto load_row = [&](int ys, Row &r) {
-        if (FROM_INPUT) {
-            int cy = hl::clampi(ys, f.in_y0, f.in_y0 + f.in_h - 1) - f.in_y0;
-            int64_t ro = (int64_t)cy * f.in_sy;
-            float f0 = __fmul_rn((float)__ldg(in0 + ro), hl::kInv65535);
-            float f1 = __fmul_rn((float)__ldg(in1 + ro), hl::kInv65535);
-            float f2_ = __fmul_rn((float)__ldg(in2 + ro), hl::kInv65535);
-            float g = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, f0), __fmul_rn(0.587f, f1)), __fmul_rn(0.114f, f2_));
-            int idx = lut_index(f, g);
-            const float *lp = lut_c + idx;
-            const float2 g2 = make_float2(g, g);
-#pragma unroll
-            for (int q = 0; q < K / 2; q++) {
-                // level_k = float(k) * (1/(levels-1)); gP0 = beta*(g - level_k) + level_k + remap(idx - 256k).
-                // The two inexact multiplies stay scalar __fmul_rn: ptxas fuses a packed mul feeding a packed add
-                // into FFMA2 (single rounding) even with explicit .rn, which breaks bit-exactness.
-                float2 lvl = make_float2(__fmul_rn((float)(2 * q), f.inv_lm1), __fmul_rn((float)(2 * q + 1), f.inv_lm1));
-                float2 gm = hl::sub2(g2, lvl);
-                float2 t = make_float2(__fmul_rn(f.beta, gm.x), __fmul_rn(f.beta, gm.y));
-                float2 bg = hl::add2(t, lvl);
-                r.v[q] = hl::add2(bg, make_float2(lp[-256 * (2 * q)], lp[-256 * (2 * q + 1)]));
-            }
-            r.s = g;
-        } else {
-            int cy = hl::clampi(ys, src.sy.lo, src.sy.hi) - src.sy.lo;
-            size_t ro = (size_t)cy * src.gpitch;
-#pragma unroll
-            for (int q = 0; q < K / 4; q++) {
-                float4 t = __ldg(gcol + ro * (K / 4) + q);
-                r.v[2 * q] = make_float2(t.x, t.y);
-                r.v[2 * q + 1] = make_float2(t.z, t.w);
-            }
-            r.s = __ldg(icol + ro);
-        }
-    };
-    auto down4_2 = [](float2 a, float2 b, float2 c, float2 d) -> float2 {
-        // (a + 3*(b+c) + d) * 0.125 with every rounding of the scalar form: 3*s is formed as fma(s, 2, s) =
-        // round(2s + s) = round(3s) (2s is exact), so no packed multiply feeds a packed add (see load_row);
-        // the final *0.125 is exact, so a later fusion of it into a consumer's add cannot change bits.
-        const float2 two = make_float2(2.0f, 2.0f), eighth = make_float2(0.125f, 0.125f);
-        float2 s3 = hl::add2(b, c);
-        s3 = hl::fma2(s3, two, s3);
-        return hl::mul2(hl::add2(hl::add2(a, s3), d), eighth);
-    };
-
-    Row ra, rb, rc, rd;
-    load_row(2 * Y1 - 1, ra);
-    load_row(2 * Y1, rb);
-    const bool writer = !(lane & 1) && lane < 2 * kStripCols && (X1 + (lane >> 1)) <= dst.sx.hi;
-    const size_t dcol = (size_t)(X1 + (lane >> 1) - dst.sx.lo);
-    for (int y1 = Y1; y1 < Y1e; y1++) {
-        load_row(2 * y1 + 1, rc);
-        load_row(2 * y1 + 2, rd);
-        float2 o[K / 2];
-#pragma unroll
-        for (int q = 0; q < K / 2; q++) {
-            float2 dy = down4_2(ra.v[q], rb.v[q], rc.v[q], rd.v[q]);
-            float2 d1 = make_float2(__shfl_down_sync(0xffffffffu, dy.x, 1), __shfl_down_sync(0xffffffffu, dy.y, 1));
-            float2 d2 = make_float2(__shfl_down_sync(0xffffffffu, dy.x, 2), __shfl_down_sync(0xffffffffu, dy.y, 2));
-            float2 d3 = make_float2(__shfl_down_sync(0xffffffffu, dy.x, 3), __shfl_down_sync(0xffffffffu, dy.y, 3));
-            o[q] = down4_2(dy, d1, d2, d3);
-            ra.v[q] = rc.v[q];
-            rb.v[q] = rd.v[q];
-        }
-        float dys = down4(ra.s, rb.s, rc.s, rd.s);
-        float os = down4(dys, __shfl_down_sync(0xffffffffu, dys, 1), __shfl_down_sync(0xffffffffu, dys, 2),
-                         __shfl_down_sync(0xffffffffu, dys, 3));
-        ra.s = rc.s;
-        rb.s = rd.s;
-        if (writer) {
-            size_t pix = (size_t)(y1 - dst.sy.lo) * dst.gpitch + dcol;
-            float4 *dp = reinterpret_cast<float4 *>(dst.gp) + pix * (K / 4);
-#pragma unroll
-            for (int q = 0; q < K / 4; q++) dp[q] = make_float4(o[2 * q].x, o[2 * q].y, o[2 * q + 1].x, o[2 * q + 1].y);
-            dst.ing[pix] = os;
-        }
-    }
-}
-
-// ---- upsample helpers ---------------------------------------------------------------------------
-struct UpTaps {
-    int xa, xb, ya, yb;  // (x+1)/2, (x-1)/2, (y+1)/2, (y-1)/2 with floor division (generator :279-280)
-    float wx, wy;        // ((x%2)*2+1)/4
-};
-__device__ __forceinline__ UpTaps up_taps(int x, int y) {
-    UpTaps t;
-    t.xa = (x + 1) >> 1; t.xb = (x - 1) >> 1;
-    t.ya = (y + 1) >> 1; t.yb = (y - 1) >> 1;
-    t.wx = __fmul_rn((float)((x & 1) * 2 + 1), 0.25f);
-    t.wy = __fmul_rn((float)((y & 1) * 2 + 1), 0.25f);
-    return t;
-}
-__device__ __forceinline__ float up_combine(float faa, float fba, float fab, float fbb, float wx, float wy) {
-    // upx(x, ya) = lerp(f(xa,ya), f(xb,ya), wx); upy = lerp(upx(x,ya), upx(x,yb), wy)
-    float ua = hl::lerpf(faa, fba, wx);
-    float ub = hl::lerpf(fab, fbb, wx);
-    return hl::lerpf(ua, ub, wy);
-}
-
-// ---- K3 (v0): outGPyramid[j] for 1 <= j <= J-1 -----------------------------------------------------
-__global__ void ll_up_naive_kernel(LevelBuf cur, LevelBuf coarse, int K, float flm1, int levels, int is_top) {
-    int tx = blockIdx.x * blockDim.x + threadIdx.x;
-    int ty = blockIdx.y * blockDim.y + threadIdx.y;
-    if (tx >= cur.ox.n() || ty >= cur.oy.n()) return;
-    int x = cur.ox.lo + tx, y = cur.oy.lo + ty;
-    int sx = hl::clampi(x, cur.sx.lo, cur.sx.hi) - cur.sx.lo;
-    int sy = hl::clampi(y, cur.sy.lo, cur.sy.hi) - cur.sy.lo;
-    size_t sp = (size_t)sy * cur.gpitch + sx;
-    // split inGPyramid[j] into integer and fractional level (generator :67-69)
-    float level = __fmul_rn(cur.ing[sp], flm1);
-    int li = hl::clampi((int)level, 0, levels - 2);
-    float lf = __fsub_rn(level, (float)li);
-    float l0 = cur.gp[sp * K + li], l1 = cur.gp[sp * K + li + 1];
-    float o;
-    if (is_top) {
-        o = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, lf), l0), __fmul_rn(lf, l1));
-    } else {
-        UpTaps t = up_taps(x, y);
-        int xa = hl::clampi(t.xa, coarse.sx.lo, coarse.sx.hi) - coarse.sx.lo;
-        int xb = hl::clampi(t.xb, coarse.sx.lo, coarse.sx.hi) - coarse.sx.lo;
-        int ya = hl::clampi(t.ya, coarse.sy.lo, coarse.sy.hi) - coarse.sy.lo;
-        int yb = hl::clampi(t.yb, coarse.sy.lo, coarse.sy.hi) - coarse.sy.lo;
-        const float *paa = coarse.gp + ((size_t)ya * coarse.gpitch + xa) * K;
-        const float *pba = coarse.gp + ((size_t)ya * coarse.gpitch + xb) * K;
-        const float *pab = coarse.gp + ((size_t)yb * coarse.gpitch + xa) * K;
-        const float *pbb = coarse.gp + ((size_t)yb * coarse.gpitch + xb) * K;
-        // lPyramid[j] = gPyramid[j] - upsample(gPyramid[j+1]) (generator :53)
-        l0 = __fsub_rn(l0, up_combine(paa[li], pba[li], pab[li], pbb[li], t.wx, t.wy));
-        l1 = __fsub_rn(l1, up_combine(paa[li + 1], pba[li + 1], pab[li + 1], pbb[li + 1], t.wx, t.wy));
-        float outl = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, lf), l0), __fmul_rn(lf, l1));
-        // outGPyramid[j] = upsample(outGPyramid[j+1]) + outLPyramid[j] (generator :78)
-        int oxa = t.xa - coarse.ox.lo, oxb = t.xb - coarse.ox.lo, oya = t.ya - coarse.oy.lo, oyb = t.yb - coarse.oy.lo;
-        float u = up_combine(coarse.outg[(size_t)oya * coarse.opitch + oxa], coarse.outg[(size_t)oya * coarse.opitch + oxb],
-                             coarse.outg[(size_t)oyb * coarse.opitch + oxa], coarse.outg[(size_t)oyb * coarse.opitch + oxb],
-                             t.wx, t.wy);
-        o = __fadd_rn(u, outl);
-    }
-    cur.outg[(size_t)ty * cur.opitch + tx] = o;
-}
-
-// ---- K4 (v0): level 0 + colour + cast -----------------------------------------------------------
-__global__ void ll_final_naive_kernel(LLFrame f, LevelBuf L1, int has_coarse) {
-    int tx = blockIdx.x * blockDim.x + threadIdx.x;
-    int ty = blockIdx.y * blockDim.y + threadIdx.y;
-    if (tx >= f.W || ty >= f.H) return;
-    int x = f.out_x0 + tx, y = f.out_y0 + ty;
-    const int K = f.levels;
-    float g = gray_at(f, x, y);
-    int idx = lut_index(f, g);
-    float level = __fmul_rn(g, f.flm1);
-    int li = hl::clampi((int)level, 0, f.levels - 2);
-    float lf = __fsub_rn(level, (float)li);
-    float l0 = gp0_at(f, g, idx, li), l1 = gp0_at(f, g, idx, li + 1);
-    float og0;
-    if (has_coarse) {
-        UpTaps t = up_taps(x, y);
-        int xa = hl::clampi(t.xa, L1.sx.lo, L1.sx.hi) - L1.sx.lo;
-        int xb = hl::clampi(t.xb, L1.sx.lo, L1.sx.hi) - L1.sx.lo;
-        int ya = hl::clampi(t.ya, L1.sy.lo, L1.sy.hi) - L1.sy.lo;
-        int yb = hl::clampi(t.yb, L1.sy.lo, L1.sy.hi) - L1.sy.lo;
-        const float *paa = L1.gp + ((size_t)ya * L1.gpitch + xa) * K;
-        const float *pba = L1.gp + ((size_t)ya * L1.gpitch + xb) * K;
-        const float *pab = L1.gp + ((size_t)yb * L1.gpitch + xa) * K;
-        const float *pbb = L1.gp + ((size_t)yb * L1.gpitch + xb) * K;
-        l0 = __fsub_rn(l0, up_combine(paa[li], pba[li], pab[li], pbb[li], t.wx, t.wy));
-        l1 = __fsub_rn(l1, up_combine(paa[li + 1], pba[li + 1], pab[li + 1], pbb[li + 1], t.wx, t.wy));
-        float outl = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, lf), l0), __fmul_rn(lf, l1));
-        int oxa = t.xa - L1.ox.lo, oxb = t.xb - L1.ox.lo, oya = t.ya - L1.oy.lo, oyb = t.yb - L1.oy.lo;
-        float u = up_combine(L1.outg[(size_t)oya * L1.opitch + oxa], L1.outg[(size_t)oya * L1.opitch + oxb],
-                             L1.outg[(size_t)oyb * L1.opitch + oxa], L1.outg[(size_t)oyb * L1.opitch + oxb], t.wx, t.wy);
-        og0 = __fadd_rn(u, outl);
-    } else {
-        og0 = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, lf), l0), __fmul_rn(lf, l1));
-    }
-    // color = input * (outG0 + eps) / (gray + eps); output = u16(clamp(color, 0, 65535)) (generator :82-87)
-    const float eps = 0.01f;
-    float num = __fadd_rn(og0, eps), den = __fadd_rn(g, eps);
-    const uint16_t *ip = f.in + (int64_t)(y - f.in_y0) * f.in_sy + (x - f.in_x0);
-    uint16_t *op = f.out + (int64_t)ty * f.out_sy + tx;
-    for (int c = 0; c < f.C; c++) {
-        int ca = f.out_c0 + c;  // absolute channel; the unclamped input(x,y,c) is read here
-        float v = __fdiv_rn(__fmul_rn((float)ip[(int64_t)(ca - f.in_c0) * f.in_sc], num), den);
-        op[(int64_t)c * f.out_sc] = (uint16_t)hl::clampf(v, 0.0f, 65535.0f);
-    }
-}
-
-// ---- K3/K4 (fast path, K == 8): tiled up-sweep / final kernel ---------------------------------------
-// One block = 64 x 16 fine pixels, 256 threads, 2 horizontally adjacent pixels per thread per row.
-// The coarse level's gPyramid tile (34 x 10 pixels x 8 planes) and outGPyramid tile are staged in
-// shared memory with coalesced 16-byte loads, plane-major ([row][plane][col], pitch 34 floats) so that
-// the data-dependent (li, li+1) plane gathers of a warp hit 32 different banks when neighbouring
-// pixels pick the same plane.  All f32 arithmetic that comes in pairs — the (li, li+1) planes of
-// lPyramid, the two pixels of a thread — uses Blackwell's packed FADD2/FMUL2/FFMA2 (per-component
-// round-to-nearest, identical results to the scalar ops) to halve the issue slots.
-// FINAL: level 0 — gray / gPyramid[0] recomputed from the uint16 frame (LUT in shared memory),
-// colour reintroduced, uint16 stored.  !FINAL: levels 1..J-2 — gPyramid[j] / inGPyramid[j] read from HBM.
-constexpr int kUpTW = 64, kUpTH = 16, kUpCW = 34, kUpCH = 10;
-
-__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
-__device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
-// Bilinear upsample tap (generator :279-280): lerp(f((x+1)/2), f((x-1)/2), ((x%2)*2+1)/4) always weights
-// the sample P = floor(x/2) by 0.75 and its neighbour Q = P-1 (x even) / P+1 (x odd) by 0.25.  The 0.25
-// product is exact, so zero*(1-w) + one*w == fma(f(Q), 0.25, round(0.75*f(P))) bit for bit: one FMUL2 +
-// one FFMA2 for two lanes, and no packed multiply whose fusion into an add could change a rounding.
-__device__ __forceinline__ float2 up_tap2(float2 fP, float2 fQ) {
-    return hl::fma2(fQ, f2s(0.25f), hl::mul2(fP, f2s(0.75f)));
-}
-
-template<bool FINAL>
-__global__ void __launch_bounds__(256) ll_up_tile_kernel(LLFrame f, LevelBuf cur, LevelBuf coarse) {
-    constexpr int K = 8;
-    __shared__ float s_gp[kUpCH * K * kUpCW];
-    __shared__ float s_og[kUpCH * kUpCW];
-    extern __shared__ float s_lut[];  // FINAL only
-    const int tid = threadIdx.x;
-    // fine region of this launch and this block's tile origin (absolute coordinates)
-    const int fx_lo = FINAL ? f.out_x0 : cur.ox.lo, fy_lo = FINAL ? f.out_y0 : cur.oy.lo;
-    const int fw = FINAL ? f.W : cur.ox.n(), fh = FINAL ? f.H : cur.oy.n();
-    const int X0 = fx_lo + blockIdx.x * kUpTW, Y0 = fy_lo + blockIdx.y * kUpTH;
-    const int CX0 = (X0 - 1) >> 1, CY0 = (Y0 - 1) >> 1;  // first coarse column / row of the tile
-    if (FINAL) {
-        for (int i = tid; i <= 2 * f.lut_half; i += 256) s_lut[i] = f.lut[i];
-    }
-    // stage the coarse tiles (coordinates clamped into the stored regions: exact, see ll_geom.h)
-    for (int pix = tid; pix < kUpCW * kUpCH; pix += 256) {
-        int r = pix / kUpCW, c = pix - r * kUpCW;
-        int gx = hl::clampi(CX0 + c, coarse.sx.lo, coarse.sx.hi) - coarse.sx.lo;
-        int gy = hl::clampi(CY0 + r, coarse.sy.lo, coarse.sy.hi) - coarse.sy.lo;
-        const float4 *src = reinterpret_cast<const float4 *>(coarse.gp) + ((size_t)gy * coarse.gpitch + gx) * 2;
-        float4 a = __ldg(src), b = __ldg(src + 1);
-        float *d = s_gp + (r * K) * kUpCW + c;
-        d[0 * kUpCW] = a.x; d[1 * kUpCW] = a.y; d[2 * kUpCW] = a.z; d[3 * kUpCW] = a.w;
-        d[4 * kUpCW] = b.x; d[5 * kUpCW] = b.y; d[6 * kUpCW] = b.z; d[7 * kUpCW] = b.w;
-        int ox = hl::clampi(CX0 + c, coarse.ox.lo, coarse.ox.hi) - coarse.ox.lo;
-        int oy = hl::clampi(CY0 + r, coarse.oy.lo, coarse.oy.hi) - coarse.oy.lo;
-        s_og[pix] = __ldg(coarse.outg + (size_t)oy * coarse.opitch + ox);
-    }
-    __syncthreads();
-
-    const int lane_x = (tid & 31) * 2;  // first of this thread's two pixels within the tile
-    const int warp = tid >> 5;
-    const int x0 = X0 + lane_x;         // absolute x of pixel 0; pixel 1 = x0 + 1
-    if (x0 - fx_lo >= fw) return;
-    const bool has1 = (x0 + 1 - fx_lo) < fw;
-    // horizontal taps: P = floor(x/2) (weight 0.75), Q = P -/+ 1 (weight 0.25), as tile columns
-    const int px0 = (x0 >> 1) - CX0, qx0 = px0 + ((x0 & 1) ? 1 : -1);
-    const int px1 = ((x0 + 1) >> 1) - CX0, qx1 = px1 + ((x0 & 1) ? -1 : 1);
-
-#pragma unroll
-    for (int rr = 0; rr < 2; rr++) {
-        const int ly = warp + 8 * rr;
-        const int y = Y0 + ly;
-        if (y - fy_lo >= fh) break;
-        const int py = (y >> 1) - CY0, qy = py + ((y & 1) ? 1 : -1);  // vertical taps, same rule
-
-        // ---- per-pixel level-j quantities: inG (g), the two gPyramid[j] planes (li, li+1), lf
-        float g[2], lf[2], gli[2], gli1[2];
-        int li[2];
-        float inf_[3][2];  // FINAL: float(input) per channel and pixel (reused for the colour stage)
-        if (FINAL) {
-            const uint16_t *ip = f.in + (int64_t)(y - f.in_y0) * f.in_sy + (x0 - f.in_x0);
-            const int cbase = f.out_c0 - f.in_c0;  // colour stage reads input channels out_c0 .. out_c0+C-1
-            // gray always uses absolute channels 0,1,2 clamped into the input's channel range
-            int gc[3];
-#pragma unroll
-            for (int c = 0; c < 3; c++) gc[c] = hl::clampi(c, f.in_c0, f.in_c0 + f.in_c - 1) - f.in_c0;
-            float gin[3][2];
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                const uint16_t *pc = ip + (int64_t)gc[c] * f.in_sc;
-                if (has1 && (reinterpret_cast<uintptr_t>(pc) & 3) == 0) {
-                    uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(pc));
-                    gin[c][0] = (float)(v & 0xffffu); gin[c][1] = (float)(v >> 16);
-                } else {
-                    gin[c][0] = (float)__ldg(pc); gin[c][1] = has1 ? (float)__ldg(pc + 1) : 0.f;
-                }
-            }
-            // colour-stage inputs: identical to gin when the output channels are 0..2 of a 3-channel input
-            const bool same = (cbase == 0) && (f.C == 3) && (f.in_c0 == 0) && (f.in_c >= 3);
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                if (same) {
-                    inf_[c][0] = gin[c][0]; inf_[c][1] = gin[c][1];
-                } else if (c < f.C) {
-                    const uint16_t *pc = ip + (int64_t)(cbase + c) * f.in_sc;
-                    inf_[c][0] = (float)__ldg(pc); inf_[c][1] = has1 ? (float)__ldg(pc + 1) : 0.f;
-                } else {
-                    inf_[c][0] = inf_[c][1] = 0.f;
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 2; i++) {
-                float fl0 = __fmul_rn(gin[0][i], hl::kInv65535), fl1 = __fmul_rn(gin[1][i], hl::kInv65535);
-                float fl2 = __fmul_rn(gin[2][i], hl::kInv65535);
-                g[i] = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, fl0), __fmul_rn(0.587f, fl1)), __fmul_rn(0.114f, fl2));
-            }
-        } else {
-            const int sy = hl::clampi(y, cur.sy.lo, cur.sy.hi) - cur.sy.lo;
-#pragma unroll
-            for (int i = 0; i < 2; i++) {
-                int sx = hl::clampi(x0 + i, cur.sx.lo, cur.sx.hi) - cur.sx.lo;
-                g[i] = __ldg(cur.ing + (size_t)sy * cur.gpitch + sx);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-            // level = inG * (levels-1); li = clamp(int(level), 0, levels-2); lf = level - li (generator :67-69)
-            float level = __fmul_rn(g[i], f.flm1);
-            li[i] = hl::clampi((int)level, 0, f.levels - 2);
-            float fli = (float)li[i];
-            lf[i] = __fsub_rn(level, fli);
-            if (FINAL) {
-                // gPyramid[0](x,y,k) = beta*(gray - level_k) + level_k + remap(idx - 256k) (generator :41-44)
-                int idx = hl::clampi((int)__fmul_rn(level, 256.0f), 0, (f.levels - 1) * 256);
-                float lv0 = __fmul_rn(fli, f.inv_lm1), lv1 = __fmul_rn(fli + 1.0f, f.inv_lm1);
-                float2 bg = f2(__fadd_rn(__fmul_rn(f.beta, __fsub_rn(g[i], lv0)), lv0),
-                               __fadd_rn(__fmul_rn(f.beta, __fsub_rn(g[i], lv1)), lv1));
-                const float *lp = s_lut + f.lut_half + idx - 256 * li[i];
-                gli[i] = __fadd_rn(bg.x, lp[0]);
-                gli1[i] = __fadd_rn(bg.y, lp[-256]);
-            } else {
-                const int sy = hl::clampi(y, cur.sy.lo, cur.sy.hi) - cur.sy.lo;
-                int sx = hl::clampi(x0 + i, cur.sx.lo, cur.sx.hi) - cur.sx.lo;
-                const float *gp = cur.gp + ((size_t)sy * cur.gpitch + sx) * K + li[i];
-                gli[i] = __ldg(gp);
-                gli1[i] = __ldg(gp + 1);
-            }
-        }
-
-        // ---- outLPyramid[j] = (1-lf)*lP(li) + lf*lP(li+1), lP = gP[j] - upsample(gP[j+1]) (generator :53,71)
-        float outl[2];
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-            const int px = i ? px1 : px0, qx = i ? qx1 : qx0;
-            const float *rp = s_gp + (py * K + li[i]) * kUpCW;  // row P, plane li (plane li+1 is kUpCW further)
-            const float *rq = s_gp + (qy * K + li[i]) * kUpCW;  // row Q
-            float2 up_p = up_tap2(f2(rp[px], rp[kUpCW + px]), f2(rp[qx], rp[kUpCW + qx]));  // upx on row P
-            float2 up_q = up_tap2(f2(rq[px], rq[kUpCW + px]), f2(rq[qx], rq[kUpCW + qx]));  // upx on row Q
-            float2 u = up_tap2(up_p, up_q);                                                // upy
-            float2 l = hl::sub2(f2(gli[i], gli1[i]), u);
-            outl[i] = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, lf[i]), l.x), __fmul_rn(lf[i], l.y));
-        }
-        // ---- outGPyramid[j] = upsample(outGPyramid[j+1]) + outLPyramid[j] (generator :78), both pixels packed
-        const float *op_ = s_og + py * kUpCW, *oq_ = s_og + qy * kUpCW;
-        float2 ou_p = up_tap2(f2(op_[px0], op_[px1]), f2(op_[qx0], op_[qx1]));
-        float2 ou_q = up_tap2(f2(oq_[px0], oq_[px1]), f2(oq_[qx0], oq_[qx1]));
-        float2 og = hl::add2(up_tap2(ou_p, ou_q), f2(outl[0], outl[1]));
-
-        if (!FINAL) {
-            float *op = cur.outg + (size_t)(y - cur.oy.lo) * cur.opitch + (x0 - cur.ox.lo);
-            if (has1 && (reinterpret_cast<uintptr_t>(op) & 7) == 0) {
-                *reinterpret_cast<float2 *>(op) = og;
-            } else {
-                op[0] = og.x;
-                if (has1) op[1] = og.y;
-            }
-        } else {
-            // color = input * (outG0 + eps) / (gray + eps); output = u16(clamp(color, 0, 65535)) (generator :82-87)
-            const float2 eps2 = f2s(0.01f);
-            float2 num = hl::add2(og, eps2), den = hl::add2(f2(g[0], g[1]), eps2);
-            uint16_t *op = f.out + (int64_t)(y - f.out_y0) * f.out_sy + (x0 - f.out_x0);
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                if (c < f.C) {
-                    float2 prod = hl::mul2(f2(inf_[c][0], inf_[c][1]), num);
-                    float v0 = hl::clampf(__fdiv_rn(prod.x, den.x), 0.0f, 65535.0f);
-                    float v1 = hl::clampf(__fdiv_rn(prod.y, den.y), 0.0f, 65535.0f);
-                    uint16_t *pc = op + (int64_t)c * f.out_sc;
-                    uint32_t u0 = (uint32_t)v0, u1 = (uint32_t)v1;
-                    if (has1 && (reinterpret_cast<uintptr_t>(pc) & 3) == 0) {
-                        *reinterpret_cast<uint32_t *>(pc) = u0 | (u1 << 16);
-                    } else {
-                        pc[0] = (uint16_t)u0;
-                        if (has1) pc[1] = (uint16_t)u1;
-                    }
-                }
-            }
-        }
-    }
-}
+using namespace llk;
 
 int g_force_naive = 0;  // test hook bitmask (halide_b200_ll_force_generic): 1 = generic down kernels, 2 = generic up, 4 = generic final
 
@@ -606,11 +47,22 @@ const halide_filter_metadata_t kMeta = {1, 5, kArgs, "x86-64-linux-cuda-cuda_cap
 const halide_filter_metadata_t kMetaAuto = {1, 5, kArgs, "x86-64-linux-cuda-cuda_capability_100-b200_native",
                                             "local_laplacian_auto_schedule"};
 
-int run_local_laplacian(halide_buffer_t *input, int levels, float alpha, float beta, halide_buffer_t *output) {
+
+// Everything one call needs on the device: frame description + per-level buffers.
+struct Plan {
+    LLFrame f;
+    LevelSet ls;
+    ll::Geom geom;
+    int J, K;
+    float alpha;
+    float *lut;
+};
+
+int check_and_query(halide_buffer_t *input, int levels, halide_buffer_t *output, bool *done) {
     int r;
+    *done = true;
     if ((r = hb::check_arg(input, kIn))) return r;
     if ((r = hb::check_arg(output, kOut))) return r;
-
     // Bounds query: the only access that bypasses repeat_edge is input(x,y,c) in `color`
     // (generator :84), so the input must cover exactly the output region.
     bool query = false;
@@ -627,7 +79,6 @@ int run_local_laplacian(halide_buffer_t *input, int levels, float alpha, float b
         }
     }
     if (query) return 0;
-
     if ((r = hb::check_shape(input, kIn))) return r;
     if ((r = hb::check_shape(output, kOut))) return r;
     for (int d = 0; d < 3; d++) {
@@ -638,110 +89,308 @@ int run_local_laplacian(halide_buffer_t *input, int levels, float alpha, float b
         return hb::fail(levels < 2 ? halide_error_code_param_too_small : halide_error_code_param_too_large,
                         "Parameter levels is %d but must be in [2, 32]", levels);
     }
-    const int W = output->dim[0].extent, H = output->dim[1].extent, C = output->dim[2].extent;
-    if (W <= 0 || H <= 0 || C <= 0) return 0;
+    if (output->dim[0].extent <= 0 || output->dim[1].extent <= 0 || output->dim[2].extent <= 0) return 0;
+    *done = false;
+    return 0;
+}
 
-    void *din = nullptr, *dout = nullptr;
-    if ((r = hb::acquire_input(input, kIn, &din))) return r;
-    if ((r = hb::acquire_output(output, kOut, &dout))) return r;
-
-    const int J = ll::kMaxJ;
-    const int K = levels;
-    Span outx = {output->dim[0].min, output->dim[0].min + W - 1}, outy = {output->dim[1].min, output->dim[1].min + H - 1};
-    Span inx = {input->dim[0].min, input->dim[0].min + input->dim[0].extent - 1};
-    Span iny = {input->dim[1].min, input->dim[1].min + input->dim[1].extent - 1};
-    ll::Geom geom = ll::make_geom(outx, outy, inx, iny, J);
-
-    hb::Scratch scratch;
-    LLFrame f;
+void fill_frame(Plan &p, halide_buffer_t *input, halide_buffer_t *output, void *din, void *dout, int levels, float alpha,
+                float beta) {
+    LLFrame &f = p.f;
     f.in = (const uint16_t *)din;
     f.in_sy = input->dim[1].stride; f.in_sc = input->dim[2].stride;
     f.in_x0 = input->dim[0].min; f.in_y0 = input->dim[1].min; f.in_c0 = input->dim[2].min;
     f.in_w = input->dim[0].extent; f.in_h = input->dim[1].extent; f.in_c = input->dim[2].extent;
+    f.clamp_y0 = f.in_y0; f.clamp_h = f.in_h;
+    f.halo_top = f.halo_bot = nullptr;
+    f.halo_top_rows = f.halo_bot_rows = f.halo_pitch = 0;
     f.out = (uint16_t *)dout;
     f.out_sy = output->dim[1].stride; f.out_sc = output->dim[2].stride;
     f.out_x0 = output->dim[0].min; f.out_y0 = output->dim[1].min; f.out_c0 = output->dim[2].min;
-    f.W = W; f.H = H; f.C = C;
+    f.W = output->dim[0].extent; f.H = output->dim[1].extent; f.C = output->dim[2].extent;
     f.levels = levels;
     f.beta = beta;
     f.flm1 = (float)(levels - 1);
     f.inv_lm1 = 1.0f / (float)(levels - 1);
     f.lut_half = 256 * (levels - 1);
-    float *lut = scratch.get<float>(2 * f.lut_half + 1);
-    if (!lut) return hb::fail(halide_error_code_device_malloc_failed, "local_laplacian: scratch allocation failed");
-    f.lut = lut;
+    p.K = levels;
+    p.J = ll::kMaxJ;
+    p.alpha = alpha;
+}
 
-    LevelBuf lb[ll::kMaxJ];
-    for (int j = 1; j < J; j++) {
-        const ll::Level &lv = geom.lv[j];
-        lb[j].sx = lv.sx; lb[j].sy = lv.sy; lb[j].ox = lv.ox; lb[j].oy = lv.oy;
-        lb[j].gpitch = lv.gpitch; lb[j].opitch = lv.opitch;
+int alloc_levels(Plan &p, hb::Scratch &scratch) {
+    p.lut = scratch.get<float>(2 * p.f.lut_half + 1);
+    if (!p.lut) return hb::fail(halide_error_code_device_malloc_failed, "local_laplacian: scratch allocation failed");
+    p.f.lut = p.lut;
+    for (int j = 1; j < p.J; j++) {
+        const ll::Level &lv = p.geom.lv[j];
+        LevelBuf &b = p.ls.lv[j];
+        b.sx = lv.sx; b.sy = lv.sy; b.ox = lv.ox; b.oy = lv.oy;
+        b.cy = lv.cy; b.coy = lv.coy; b.gy = lv.gy;
+        b.gpitch = lv.gpitch; b.opitch = lv.opitch;
         size_t gpix = (size_t)lv.sy.n() * lv.gpitch;
-        lb[j].gp = scratch.get<float>(gpix * K);
-        lb[j].ing = scratch.get<float>(gpix);
-        lb[j].outg = scratch.get<float>((size_t)lv.oy.n() * lv.opitch);
-        if (!lb[j].gp || !lb[j].ing || !lb[j].outg) {
+        b.gp = scratch.get<float>(gpix * p.K);
+        b.ing = scratch.get<float>(gpix);
+        b.outg = scratch.get<float>((size_t)lv.oy.n() * lv.opitch);
+        if (!b.gp || !b.ing || !b.outg) {
             return hb::fail(halide_error_code_device_malloc_failed, "local_laplacian: scratch allocation failed");
         }
     }
+    p.ls.lv[0] = p.ls.lv[1];  // level 0 is never stored; keep the slot initialised
+    return 0;
+}
+
+// ---- launch helpers ------------------------------------------------------------------------------------
+const dim3 kBlk(32, 8);
+dim3 grid_for(int w, int h) { return dim3((w + 31) / 32, (h + 7) / 8); }
+
+int strip_rows(const LevelBuf &d) {
+    // tall strips amortise the 2-row apron; shrink them when the level is too small to fill 148 SMs
+    int rows = 16;
+    int sx = (d.sx.n() + kStripCols - 1) / kStripCols;
+    while (rows > 2 && (int64_t)((sx + 3) / 4) * ((d.cy.n() + rows - 1) / rows) < 148 * 4) rows >>= 1;
+    return rows;
+}
+dim3 strip_grid(const LevelBuf &d, int rows) {
+    int sx = (d.sx.n() + kStripCols - 1) / kStripCols;
+    return dim3((sx + 3) / 4, (d.cy.n() + rows - 1) / rows);
+}
+
+void launch_lut(Plan &p, cudaStream_t s) {
+    HB_LAUNCH("ll_lut", ll_lut_kernel, (2 * p.f.lut_half + 1 + 255) / 256, 256, 0, s, p.lut, p.f.lut_half, p.alpha);
+}
+
+void launch_down(Plan &p, int j, cudaStream_t s) {  // produce level j (j >= 1) rows cy
+    LevelBuf *lb = p.ls.lv;
+    if (lb[j].cy.n() <= 0) return;
+    const bool fast = (p.K == 8) && !(g_force_naive & 1);
+    if (j == 1) {
+        if (fast) {
+            int rows = strip_rows(lb[1]);
+            size_t smem = (size_t)(2 * p.f.lut_half + 1) * sizeof(float);
+            HB_LAUNCH("ll_level1_strip", (ll_down_strip_kernel<8, true>), strip_grid(lb[1], rows), 128, smem, s, p.f, lb[1],
+                      lb[1], rows);
+        } else {
+            HB_LAUNCH("ll_level1", ll_level1_naive_kernel, grid_for(lb[1].sx.n(), lb[1].cy.n()), kBlk, 0, s, p.f, lb[1]);
+        }
+    } else if (fast) {
+        int rows = strip_rows(lb[j]);
+        HB_LAUNCH("ll_down_strip", (ll_down_strip_kernel<8, false>), strip_grid(lb[j], rows), 128, 0, s, p.f, lb[j - 1], lb[j],
+                  rows);
+    } else {
+        HB_LAUNCH("ll_down", ll_down_naive_kernel, grid_for(lb[j].sx.n(), lb[j].cy.n()), kBlk, 0, s, lb[j - 1], lb[j], p.K);
+    }
+}
+
+void launch_up(Plan &p, int j, cudaStream_t s) {  // produce outGPyramid[j] (1 <= j <= J-1) rows coy
+    LevelBuf *lb = p.ls.lv;
+    if (lb[j].coy.n() <= 0) return;
+    const bool fast_up = (p.K == 8) && !(g_force_naive & 2);
+    if (fast_up && j < p.J - 1) {
+        dim3 g((lb[j].ox.n() + kUpTW - 1) / kUpTW, (lb[j].coy.n() + kUpTH - 1) / kUpTH);
+        HB_LAUNCH("ll_up_tile", (ll_up_tile_kernel<false>), g, 256, 0, s, p.f, lb[j], lb[j + 1]);
+    } else {
+        HB_LAUNCH("ll_up", ll_up_naive_kernel, grid_for(lb[j].ox.n(), lb[j].coy.n()), kBlk, 0, s, lb[j],
+                  lb[j == p.J - 1 ? j : j + 1], p.K, p.f.flm1, p.f.levels, j == p.J - 1 ? 1 : 0);
+    }
+}
+
+void launch_final(Plan &p, cudaStream_t s) {
+    LevelBuf *lb = p.ls.lv;
+    if (p.J > 1 && p.K == 8 && !(g_force_naive & 4) && p.f.C <= 3) {
+        dim3 g((p.f.W + kUpTW - 1) / kUpTW, (p.f.H + kUpTH - 1) / kUpTH);
+        size_t smem = (size_t)(2 * p.f.lut_half + 1) * sizeof(float);
+        HB_LAUNCH("ll_final_tile", (ll_up_tile_kernel<true>), g, 256, smem, s, p.f, lb[1], lb[1]);
+    } else {
+        HB_LAUNCH("ll_final", ll_final_naive_kernel, grid_for(p.f.W, p.f.H), kBlk, 0, s, p.f, lb[1], p.J > 1 ? 1 : 0);
+    }
+}
+
+// Coarse tail in one cooperative launch: levels j0+1 .. J-1 down and up (see ll_coarse_fused_kernel).
+bool launch_coarse_fused(Plan &p, int j0, cudaStream_t s) {
+    static int max_blocks = -1;
+    if (max_blocks < 0) {
+        int dev = 0, sms = 0, coop = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ll_coarse_fused_kernel, 256, 0);
+        max_blocks = coop ? sms * (per_sm > 2 ? 2 : per_sm) : 0;
+    }
+    if (max_blocks <= 0) return false;
+    int J = p.J, K = p.K, levels = p.f.levels;
+    float flm1 = p.f.flm1;
+    void *args[] = {&p.ls, &J, &j0, &K, &flm1, &levels};
+    hb::count_launch("ll_coarse_fused", s);
+    cudaError_t e = cudaLaunchCooperativeKernel((void *)ll_coarse_fused_kernel, dim3(max_blocks), dim3(256), args, 0, s);
+    hb::after_launch(s);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return true;
+}
+
+int run_local_laplacian(halide_buffer_t *input, int levels, float alpha, float beta, halide_buffer_t *output) {
+    int r;
+    bool done;
+    if ((r = check_and_query(input, levels, output, &done)) || done) return r;
+    void *din = nullptr, *dout = nullptr;
+    if ((r = hb::acquire_input(input, kIn, &din))) return r;
+    if ((r = hb::acquire_output(output, kOut, &dout))) return r;
+
+    Plan p;
+    fill_frame(p, input, output, din, dout, levels, alpha, beta);
+    const int W = p.f.W, H = p.f.H;
+    Span outx = {p.f.out_x0, p.f.out_x0 + W - 1}, outy = {p.f.out_y0, p.f.out_y0 + H - 1};
+    Span inx = {p.f.in_x0, p.f.in_x0 + p.f.in_w - 1}, iny = {p.f.in_y0, p.f.in_y0 + p.f.in_h - 1};
+    p.geom = ll::make_geom(outx, outy, inx, iny, p.J);
+    hb::Scratch scratch;
+    if ((r = alloc_levels(p, scratch))) return r;
 
     cudaStream_t s = hb::stream();
     {
         hb::CallTimer timer(s);
-        HB_LAUNCH("ll_lut", ll_lut_kernel, (2 * f.lut_half + 1 + 255) / 256, 256, 0, s, lut, f.lut_half, alpha);
-        dim3 blk(32, 8);
-        auto grid_for = [&](int w, int h) { return dim3((w + 31) / 32, (h + 7) / 8); };
-        if (J > 1) {
-            const bool fast = (K == 8) && !(g_force_naive & 1);
-            const bool fast_up = (K == 8) && !(g_force_naive & 2);
-            auto strip_rows = [&](const LevelBuf &d) {
-                // tall strips amortise the 2-row apron; shrink them when the level is too small to fill 148 SMs
-                int rows = 16;
-                int sx = (d.sx.n() + kStripCols - 1) / kStripCols;
-                while (rows > 2 && (int64_t)((sx + 3) / 4) * ((d.sy.n() + rows - 1) / rows) < 148 * 4) rows >>= 1;
-                return rows;
-            };
-            auto strip_grid = [&](const LevelBuf &d, int rows) {
-                int sx = (d.sx.n() + kStripCols - 1) / kStripCols;
-                return dim3((sx + 3) / 4, (d.sy.n() + rows - 1) / rows);
-            };
-            if (fast) {
-                int rows = strip_rows(lb[1]);
-                size_t smem = (size_t)(2 * f.lut_half + 1) * sizeof(float);
-                HB_LAUNCH("ll_level1_strip", (ll_down_strip_kernel<8, true>), strip_grid(lb[1], rows), 128, smem, s, f, lb[1],
-                          lb[1], rows);
-            } else {
-                HB_LAUNCH("ll_level1", ll_level1_naive_kernel, grid_for(lb[1].sx.n(), lb[1].sy.n()), blk, 0, s, f, lb[1]);
-            }
-            for (int j = 2; j < J; j++) {
-                if (fast) {
-                    int rows = strip_rows(lb[j]);
-                    HB_LAUNCH("ll_down_strip", (ll_down_strip_kernel<8, false>), strip_grid(lb[j], rows), 128, 0, s, f,
-                              lb[j - 1], lb[j], rows);
-                } else {
-                    HB_LAUNCH("ll_down", ll_down_naive_kernel, grid_for(lb[j].sx.n(), lb[j].sy.n()), blk, 0, s, lb[j - 1],
-                              lb[j], K);
-                }
-            }
-            for (int j = J - 1; j >= 1; j--) {
-                if (fast_up && j < J - 1) {
-                    dim3 g((lb[j].ox.n() + kUpTW - 1) / kUpTW, (lb[j].oy.n() + kUpTH - 1) / kUpTH);
-                    HB_LAUNCH("ll_up_tile", (ll_up_tile_kernel<false>), g, 256, 0, s, f, lb[j], lb[j + 1]);
-                } else {
-                    HB_LAUNCH("ll_up", ll_up_naive_kernel, grid_for(lb[j].ox.n(), lb[j].oy.n()), blk, 0, s, lb[j],
-                              lb[j == J - 1 ? j : j + 1], K, f.flm1, levels, j == J - 1 ? 1 : 0);
-                }
-            }
+        launch_lut(p, s);
+        // Levels whose pixel count is small are launch-latency bound: they run in one cooperative kernel.
+        int j0 = p.J - 1;
+        if (!(g_force_naive & 8)) {
+            while (j0 > 1 && (int64_t)p.ls.lv[j0].sx.n() * p.ls.lv[j0].sy.n() <= 160 * 1024) j0--;
         }
-        if (J > 1 && K == 8 && !(g_force_naive & 4) && C <= 3) {
-            dim3 g((W + kUpTW - 1) / kUpTW, (H + kUpTH - 1) / kUpTH);
-            size_t smem = (size_t)(2 * f.lut_half + 1) * sizeof(float);
-            HB_LAUNCH("ll_final_tile", (ll_up_tile_kernel<true>), g, 256, smem, s, f, lb[1], lb[1]);
-        } else {
-            HB_LAUNCH("ll_final", ll_final_naive_kernel, grid_for(W, H), blk, 0, s, f, lb[1], J > 1 ? 1 : 0);
+        // j0 = last level produced by its own launch; levels j0+1.. are fused (if any)
+        bool fused = false;
+        for (int j = 1; j <= j0; j++) launch_down(p, j, s);
+        if (j0 < p.J - 1) fused = launch_coarse_fused(p, j0, s);
+        if (!fused) {
+            for (int j = j0 + 1; j < p.J; j++) launch_down(p, j, s);
+            for (int j = p.J - 1; j > j0; j--) launch_up(p, j, s);
         }
+        for (int j = j0; j >= 1; j--) launch_up(p, j, s);
+        launch_final(p, s);
     }
     if ((r = hb::check_cuda(cudaGetLastError(), "local_laplacian launch", halide_error_code_device_run_failed))) return r;
+    hb::mark_output_written(output);
+    return 0;
+}
+
+// ---- row-sharded variant (one process per GPU) -----------------------------------------------------------
+// `input`/`output` describe this rank's band: all columns and channels of the frame, rows
+// [dim[1].min, dim[1].min + extent) in the frame's coordinates.  frame_y_min/extent give the rows of the whole
+// frame; ranks must be ordered top to bottom (rank r-1 holds the rows directly above rank r's).
+// One halo exchange per pyramid level in each sweep plus one for the input rows.
+int run_local_laplacian_sharded(halide_buffer_t *input, int levels, float alpha, float beta, halide_buffer_t *output,
+                                int frame_y_min, int frame_y_extent) {
+    int r;
+    bool done;
+    if ((r = check_and_query(input, levels, output, &done)) || done) return r;
+    if (!hbdist::active()) {
+        return hb::fail(halide_error_code_generic_error, "local_laplacian_sharded: call halide_b200_dist_init first");
+    }
+    if (levels != 8) {
+        return hb::fail(halide_error_code_unimplemented, "local_laplacian_sharded: only levels == 8 is built for sharding");
+    }
+    const int rank = hbdist::rank(), nranks = hbdist::size();
+    Span band = {output->dim[1].min, output->dim[1].min + output->dim[1].extent - 1};
+    if (input->dim[1].min != band.lo || input->dim[1].extent != band.n()) {
+        return hb::fail(halide_error_code_constraint_violated,
+                        "local_laplacian_sharded: input rows [%d,%d) must equal the output band [%d,%d)", input->dim[1].min,
+                        input->dim[1].min + input->dim[1].extent, band.lo, band.hi + 1);
+    }
+    const bool first = rank == 0, last = rank == nranks - 1;
+    Span frame_y = {frame_y_min, frame_y_min + frame_y_extent - 1};
+    if ((first && band.lo != frame_y.lo) || (last && band.hi != frame_y.hi) || band.lo < frame_y.lo || band.hi > frame_y.hi) {
+        return hb::fail(halide_error_code_constraint_violated, "local_laplacian_sharded: band [%d,%d] inconsistent with frame rows [%d,%d] on rank %d/%d",
+                        band.lo, band.hi, frame_y.lo, frame_y.hi, rank, nranks);
+    }
+    void *din = nullptr, *dout = nullptr;
+    if ((r = hb::acquire_input(input, kIn, &din))) return r;
+    if ((r = hb::acquire_output(output, kOut, &dout))) return r;
+
+    Plan p;
+    fill_frame(p, input, output, din, dout, levels, alpha, beta);
+    const int W = p.f.W;
+    Span outx = {p.f.out_x0, p.f.out_x0 + W - 1};
+    Span inx = {p.f.in_x0, p.f.in_x0 + p.f.in_w - 1};
+    ll::Geom whole = ll::make_geom(outx, frame_y, inx, frame_y, p.J);
+    ll::BandLevel bl[ll::kMaxJ];
+    ll::compute_band_y(whole, band, first, last, bl);
+    for (int j = 1; j < p.J; j++) {
+        if (bl[j].own.n() < 2 || bl[j].own_o.n() < 1) {
+            return hb::fail(halide_error_code_constraint_violated,
+                            "local_laplacian_sharded: band of %d rows is too small for %d pyramid levels (level %d owns %d rows)",
+                            band.n(), p.J, j, bl[j].own.n());
+        }
+    }
+    p.geom = ll::make_band_geom(whole, bl);
+    p.f.clamp_y0 = frame_y.lo;
+    p.f.clamp_h = frame_y.n();
+    hb::Scratch scratch;
+    if ((r = alloc_levels(p, scratch))) return r;
+    // input halo: 1 row above, 2 rows below (the 1-3-3-1 taps of level 1), per channel, x relative to in_x0
+    const int ht = first ? 0 : 1, hbn = last ? 0 : 2, C = p.f.in_c;
+    uint16_t *halo_top = nullptr, *halo_bot = nullptr;
+    p.f.halo_pitch = p.f.in_w;
+    if (ht) halo_top = scratch.get<uint16_t>((size_t)C * ht * p.f.in_w);
+    if (hbn) halo_bot = scratch.get<uint16_t>((size_t)C * hbn * p.f.in_w);
+    if ((ht && !halo_top) || (hbn && !halo_bot)) {
+        return hb::fail(halide_error_code_device_malloc_failed, "local_laplacian_sharded: scratch allocation failed");
+    }
+    p.f.halo_top = halo_top; p.f.halo_bot = halo_bot;
+    p.f.halo_top_rows = ht; p.f.halo_bot_rows = hbn;
+
+    cudaStream_t s = hb::stream();
+    hbdist::Msg msgs[64];
+    const int up = rank - 1, dn = rank + 1;
+    auto exchange_rows_f32 = [&](float *base, size_t row_elems, Span stored, Span own, int n_up, int n_dn_recv) -> int {
+        // send my first n_up owned rows up / my last 1 owned row down; receive 1 row above / n_dn_recv rows below
+        int n = 0;
+        const size_t rb = row_elems * sizeof(float);
+        if (!first) {
+            msgs[n++] = {base + (size_t)(own.lo - stored.lo) * row_elems, (size_t)n_up * rb, up, true};
+            msgs[n++] = {base + (size_t)(own.lo - 1 - stored.lo) * row_elems, rb, up, false};
+        }
+        if (!last) {
+            msgs[n++] = {base + (size_t)(own.hi - stored.lo) * row_elems, rb, dn, true};
+            msgs[n++] = {base + (size_t)(own.hi + 1 - stored.lo) * row_elems, (size_t)n_dn_recv * rb, dn, false};
+        }
+        return hbdist::exchange(msgs, n, s);
+    };
+    {
+        hb::CallTimer timer(s);
+        // input rows: first two owned rows go up, last owned row goes down (per channel; rows may be strided)
+        {
+            int n = 0;
+            const size_t rb = (size_t)p.f.in_w * sizeof(uint16_t);
+            for (int c = 0; c < C; c++) {
+                uint16_t *plane = (uint16_t *)din + (int64_t)c * p.f.in_sc;
+                if (!first) {
+                    msgs[n++] = {plane, rb, up, true};
+                    msgs[n++] = {plane + p.f.in_sy, rb, up, true};
+                    msgs[n++] = {halo_top + (size_t)c * ht * p.f.in_w, rb, up, false};
+                }
+                if (!last) {
+                    msgs[n++] = {plane + (int64_t)(p.f.in_h - 1) * p.f.in_sy, rb, dn, true};
+                    msgs[n++] = {halo_bot + (size_t)c * hbn * p.f.in_w, 2 * rb, dn, false};
+                }
+            }
+            if ((r = hbdist::exchange(msgs, n, s))) return r;
+        }
+        launch_lut(p, s);
+        LevelBuf *lb = p.ls.lv;
+        for (int j = 1; j < p.J; j++) {
+            launch_down(p, j, s);
+            // gPyramid[j] + inGPyramid[j] halo: 2 rows up, 1 row down (receive 1 above, 2 below)
+            if ((r = exchange_rows_f32(lb[j].gp, (size_t)lb[j].gpitch * p.K, lb[j].sy, lb[j].cy, 2, 2))) return r;
+            if ((r = exchange_rows_f32(lb[j].ing, (size_t)lb[j].gpitch, lb[j].sy, lb[j].cy, 2, 2))) return r;
+        }
+        for (int j = p.J - 1; j >= 1; j--) {
+            launch_up(p, j, s);
+            // outGPyramid[j] halo: 1 row each way
+            if ((r = exchange_rows_f32(lb[j].outg, (size_t)lb[j].opitch, lb[j].oy, lb[j].coy, 1, 1))) return r;
+        }
+        launch_final(p, s);
+    }
+    if ((r = hb::check_cuda(cudaGetLastError(), "local_laplacian_sharded launch", halide_error_code_device_run_failed))) return r;
     hb::mark_output_written(output);
     return 0;
 }
@@ -773,4 +422,26 @@ extern "C" const halide_filter_metadata_t *local_laplacian_auto_schedule_metadat
 // Test hook: route K == 8 calls through the generic (any `levels`) kernels so both paths stay covered.
 extern "C" void halide_b200_ll_force_generic(int enable) {
     g_force_naive = enable;
+}
+
+// Row-sharded entry point (B200 extension; see run_local_laplacian_sharded).
+extern "C" int halide_b200_local_laplacian_sharded(halide_buffer_t *input, int32_t levels, float alpha, float beta,
+                                                   halide_buffer_t *output, int32_t frame_y_min, int32_t frame_y_extent) {
+    return run_local_laplacian_sharded(input, levels, alpha, beta, output, frame_y_min, frame_y_extent);
+}
+
+// Band geometry probe for the CPU-side tests of the sharding logic (no CUDA calls): fills
+// out[j*8 .. j*8+7] = {own.lo, own.hi, stored.lo, stored.hi, own_o.lo, own_o.hi, stored_o.lo, stored_o.hi}.
+extern "C" int halide_b200_ll_band_geometry(int32_t frame_w, int32_t frame_h, int32_t band_lo, int32_t band_hi, int32_t first,
+                                            int32_t last, int32_t *out) {
+    Span fx = {0, frame_w - 1}, fy = {0, frame_h - 1};
+    ll::Geom whole = ll::make_geom(fx, fy, fx, fy, ll::kMaxJ);
+    ll::BandLevel bl[ll::kMaxJ];
+    ll::compute_band_y(whole, Span{band_lo, band_hi}, first != 0, last != 0, bl);
+    for (int j = 0; j < ll::kMaxJ; j++) {
+        int32_t *o = out + j * 8;
+        o[0] = bl[j].own.lo; o[1] = bl[j].own.hi; o[2] = bl[j].stored.lo; o[3] = bl[j].stored.hi;
+        o[4] = bl[j].own_o.lo; o[5] = bl[j].own_o.hi; o[6] = bl[j].stored_o.lo; o[7] = bl[j].stored_o.hi;
+    }
+    return 0;
 }

@@ -235,6 +235,31 @@ void halide_b200_profile_enable(int enable);
 void halide_b200_profile_reset(void);
 int halide_b200_profile_report(char *out, int out_size);
 
+
+/* ---- multi-GPU (one process per GPU; the reference has no counterpart) ---- */
+
+/* NCCL bootstrap: rank 0 obtains a 128-byte id, the host's control plane broadcasts it, every rank
+ * joins.  Ranks are ordered top to bottom over the frame's rows. */
+int halide_b200_dist_unique_id(char *out128);
+int halide_b200_dist_init(int rank, int nranks, const char *id128);
+int halide_b200_dist_shutdown(void);
+int halide_b200_dist_rank(void);
+int halide_b200_dist_size(void);
+
+/* local_laplacian on this rank's row band of a frame whose rows are [frame_y_min, frame_y_min +
+ * frame_y_extent): `input`/`output` hold the band's rows (all columns/channels) with dim[1].min in
+ * frame coordinates.  One halo exchange with the row neighbours per pyramid level and sweep.
+ * Bit-identical to the single-GPU filter on the whole frame. */
+int halide_b200_local_laplacian_sharded(struct halide_buffer_t *input, int32_t levels, float alpha, float beta,
+                                        struct halide_buffer_t *output, int32_t frame_y_min, int32_t frame_y_extent);
+
+/* Host-only probe of the band geometry (rows owned / held per pyramid level) for tests; out[64]. */
+int halide_b200_ll_band_geometry(int32_t frame_w, int32_t frame_h, int32_t band_lo, int32_t band_hi, int32_t first,
+                                 int32_t last, int32_t *out);
+/* Test hook: bitmask routing levels==8 calls through the generic kernels (1 down, 2 up, 4 final,
+ * 8 no fused coarse launch) so both code paths stay covered by the parity tests. */
+void halide_b200_ll_force_generic(int mask);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,26 @@
+"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): the row-sharded local_laplacian must equal
+the single-GPU filter bit for bit on every band."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("world,w,band_h", [(2, 1000, 640), (2, 333, 517)])
+def test_sharded_local_laplacian_matches_single_gpu(world, w, band_h):
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
+           "127.0.0.1", "--master-port", "29531", os.path.join(ROOT, "tools", "dist_check.py"), str(w), str(band_h)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "mismatches=0" in out.stdout
