@@ -239,13 +239,11 @@ def run_ours(args, rank, world, local_rank):
     value = total_px / 1e6 / (ms_step / 1e3)
 
     # keep the GPU busy a little longer so the clock sampler has samples even for short runs
+    # (a fixed step count: under sharding every rank must issue the same number of exchanges)
     if len(sampler.samples) < 5:
         sampler.start()
-        t_end = time.perf_counter() + 0.3
-        i = 0
-        while time.perf_counter() < t_end:
+        for i in range(300):
             step(i)
-            i += 1
         torch.cuda.synchronize()
         sampler.stop()
 
@@ -281,15 +279,15 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- per-kernel profile for the roofline (event-bracketed launches, separate pass) --------------
     roofline, kernels = None, {}
+    hlib.profile(True)
+    hlib.profile_reset()
+    reps = 5
+    for i in range(reps):   # every rank runs the pass (halo exchanges pair up); rank 0 reports
+        step(i)
+    torch.cuda.synchronize()
+    rep = hlib.profile_report()
+    hlib.profile(False)
     if rank == 0:
-        hlib.profile(True)
-        hlib.profile_reset()
-        reps = 5
-        for i in range(reps):
-            filters.local_laplacian(bins[i % NSETS], LEVELS, ALPHA, BETA, bouts[i % NSETS]) if world == 1 else step(i)
-        torch.cuda.synchronize()
-        rep = hlib.profile_report()
-        hlib.profile(False)
         kernels = {k: {"launches_per_step": c / reps, "ms_per_step": ms / reps} for k, (c, ms) in rep.items()}
         if rep:
             top = max(rep.items(), key=lambda kv: kv[1][1])
@@ -305,7 +303,11 @@ def run_ours(args, rank, world, local_rank):
                         "pipeline_kernel_ms": pipe_ms,
                         "pipeline_frac": alg_bytes / (pipe_ms / 1e3) / 1e9 / peak}
 
+    if dist is not None:
+        dist.barrier()
     if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
         return
     cpu = cpu_oracle_rate(W, H)
     line = {"metric": "local_laplacian Mpixels/s", "value": value, "unit": "Mpixels/s", "n_gpus": world,
@@ -321,6 +323,8 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
             "kernels": kernels}
     print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def main():

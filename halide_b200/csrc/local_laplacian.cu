@@ -199,7 +199,7 @@ void launch_final(Plan &p, cudaStream_t s) {
     LevelBuf *lb = p.ls.lv;
     if (p.J > 1 && p.K == 8 && !(g_force_naive & 4) && p.f.C <= 3) {
         dim3 g((p.f.W + kUpTW - 1) / kUpTW, (p.f.H + kUpTH - 1) / kUpTH);
-        size_t smem = (size_t)(2 * p.f.lut_half + 1) * sizeof(float);
+        size_t smem = 513 * sizeof(float);
         HB_LAUNCH("ll_final_tile", (ll_up_tile_kernel<true>), g, 256, smem, s, p.f, lb[1], lb[1]);
     } else {
         HB_LAUNCH("ll_final", ll_final_naive_kernel, grid_for(p.f.W, p.f.H), kBlk, 0, s, p.f, lb[1], p.J > 1 ? 1 : 0);
@@ -255,7 +255,7 @@ int run_local_laplacian(halide_buffer_t *input, int levels, float alpha, float b
         // Levels whose pixel count is small are launch-latency bound: they run in one cooperative kernel.
         int j0 = p.J - 1;
         if (!(g_force_naive & 8)) {
-            while (j0 > 1 && (int64_t)p.ls.lv[j0].sx.n() * p.ls.lv[j0].sy.n() <= 160 * 1024) j0--;
+            while (j0 > 1 && (int64_t)p.ls.lv[j0].sx.n() * p.ls.lv[j0].sy.n() <= 40 * 1024) j0--;
         }
         // j0 = last level produced by its own launch; levels j0+1.. are fused (if any)
         bool fused = false;
@@ -370,7 +370,9 @@ int run_local_laplacian_sharded(halide_buffer_t *input, int levels, float alpha,
                 }
                 if (!last) {
                     msgs[n++] = {plane + (int64_t)(p.f.in_h - 1) * p.f.in_sy, rb, dn, true};
-                    msgs[n++] = {halo_bot + (size_t)c * hbn * p.f.in_w, 2 * rb, dn, false};
+                    // two receives: the neighbour sends its two (possibly strided) rows as two messages
+                    msgs[n++] = {halo_bot + (size_t)c * hbn * p.f.in_w, rb, dn, false};
+                    msgs[n++] = {halo_bot + ((size_t)c * hbn + 1) * p.f.in_w, rb, dn, false};
                 }
             }
             if ((r = hbdist::exchange(msgs, n, s))) return r;
@@ -444,4 +446,20 @@ extern "C" int halide_b200_ll_band_geometry(int32_t frame_w, int32_t frame_h, in
         o[4] = bl[j].own_o.lo; o[5] = bl[j].own_o.hi; o[6] = bl[j].stored_o.lo; o[7] = bl[j].stored_o.hi;
     }
     return 0;
+}
+
+// Device self-test of the arithmetic shortcuts used by the fast kernels (shared-reciprocal division, magic-number
+// conversions): returns the number of mismatches against div.rn / cvt over n pseudo-random operand sets, or -1.
+extern "C" long long halide_b200_selftest_arith(unsigned long long n, unsigned long long seed) {
+    unsigned long long *bad = nullptr, host = 0;
+    if (cudaMalloc(&bad, sizeof(*bad)) != cudaSuccess) return -1;
+    cudaMemset(bad, 0, sizeof(*bad));
+    cudaStream_t s = hb::stream();
+    HB_LAUNCH("ll_selftest", ll_selftest_kernel, 148 * 8, 256, 0, s, n, seed, bad);
+    if (cudaMemcpyAsync(&host, bad, sizeof(host), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+        cudaFree(bad);
+        return -1;
+    }
+    cudaFree(bad);
+    return (long long)host;
 }
