@@ -123,6 +123,7 @@ def cpu_oracle_rate(W, H, budget_s=12.0, max_steps=8):
     """Time the CPU oracle on full frames of the workload (bounded sample)."""
     import numpy as np
     from oracle import pyoracle
+    pyoracle.use_all_cores()
     rng = np.random.default_rng(0)
     img = rng.integers(0, 65536, (3, H, W), dtype=np.uint16)
     pyoracle.local_laplacian(img, LEVELS, ALPHA, BETA)  # warm-up (page faults, thread pool)
@@ -144,6 +145,7 @@ def run_reference(args, rank, world):
         return
     import numpy as np
     from oracle import pyoracle
+    pyoracle.use_all_cores()
     W, H = WORKLOADS[args.workload]
     # bounded sample: a band of rows such that the whole run stays within a few minutes
     rows = H

@@ -524,6 +524,17 @@ halide_error_handler_t halide_set_error_handler(halide_error_handler_t handler) 
     return g_handler.exchange(handler);
 }
 
+// Host allocator hooks (HalideRuntime.h halide_set_custom_malloc/free; tools/halide_malloc_trace.h installs tracing
+// versions through them).  The filters allocate no host memory, so the hooks are only recorded.
+static std::atomic<halide_malloc_t> g_malloc{nullptr};
+static std::atomic<halide_free_t> g_free{nullptr};
+halide_malloc_t halide_set_custom_malloc(halide_malloc_t user_malloc) {
+    return g_malloc.exchange(user_malloc);
+}
+halide_free_t halide_set_custom_free(halide_free_t user_free) {
+    return g_free.exchange(user_free);
+}
+
 int halide_device_malloc(void *uc, halide_buffer_t *buf, const halide_device_interface_t *iface) {
     if (!iface) iface = &g_cuda_interface;
     return iface->device_malloc(uc, buf, iface);

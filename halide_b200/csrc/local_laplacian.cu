@@ -341,19 +341,24 @@ int run_local_laplacian_sharded(halide_buffer_t *input, int levels, float alpha,
     cudaStream_t s = hb::stream();
     hbdist::Msg msgs[64];
     const int up = rank - 1, dn = rank + 1;
-    auto exchange_rows_f32 = [&](float *base, size_t row_elems, Span stored, Span own, int n_up, int n_dn_recv) -> int {
-        // send my first n_up owned rows up / my last 1 owned row down; receive 1 row above / n_dn_recv rows below
-        int n = 0;
+    // queue the halo messages of one row-major f32 array: my first n_up owned rows go up and my last owned row goes
+    // down; one row arrives above and n_dn_recv rows arrive below
+    int nq = 0;
+    auto queue_rows_f32 = [&](float *base, size_t row_elems, Span stored, Span own, int n_up, int n_dn_recv) {
         const size_t rb = row_elems * sizeof(float);
         if (!first) {
-            msgs[n++] = {base + (size_t)(own.lo - stored.lo) * row_elems, (size_t)n_up * rb, up, true};
-            msgs[n++] = {base + (size_t)(own.lo - 1 - stored.lo) * row_elems, rb, up, false};
+            msgs[nq++] = {base + (size_t)(own.lo - stored.lo) * row_elems, (size_t)n_up * rb, up, true};
+            msgs[nq++] = {base + (size_t)(own.lo - 1 - stored.lo) * row_elems, rb, up, false};
         }
         if (!last) {
-            msgs[n++] = {base + (size_t)(own.hi - stored.lo) * row_elems, rb, dn, true};
-            msgs[n++] = {base + (size_t)(own.hi + 1 - stored.lo) * row_elems, (size_t)n_dn_recv * rb, dn, false};
+            msgs[nq++] = {base + (size_t)(own.hi - stored.lo) * row_elems, rb, dn, true};
+            msgs[nq++] = {base + (size_t)(own.hi + 1 - stored.lo) * row_elems, (size_t)n_dn_recv * rb, dn, false};
         }
-        return hbdist::exchange(msgs, n, s);
+    };
+    auto flush = [&]() -> int {
+        int rr = hbdist::exchange(msgs, nq, s);
+        nq = 0;
+        return rr;
     };
     {
         hb::CallTimer timer(s);
@@ -382,13 +387,15 @@ int run_local_laplacian_sharded(halide_buffer_t *input, int levels, float alpha,
         for (int j = 1; j < p.J; j++) {
             launch_down(p, j, s);
             // gPyramid[j] + inGPyramid[j] halo: 2 rows up, 1 row down (receive 1 above, 2 below)
-            if ((r = exchange_rows_f32(lb[j].gp, (size_t)lb[j].gpitch * p.K, lb[j].sy, lb[j].cy, 2, 2))) return r;
-            if ((r = exchange_rows_f32(lb[j].ing, (size_t)lb[j].gpitch, lb[j].sy, lb[j].cy, 2, 2))) return r;
+            queue_rows_f32(lb[j].gp, (size_t)lb[j].gpitch * p.K, lb[j].sy, lb[j].cy, 2, 2);
+            queue_rows_f32(lb[j].ing, (size_t)lb[j].gpitch, lb[j].sy, lb[j].cy, 2, 2);
+            if ((r = flush())) return r;  // one ncclGroup per level
         }
         for (int j = p.J - 1; j >= 1; j--) {
             launch_up(p, j, s);
             // outGPyramid[j] halo: 1 row each way
-            if ((r = exchange_rows_f32(lb[j].outg, (size_t)lb[j].opitch, lb[j].oy, lb[j].coy, 1, 1))) return r;
+            queue_rows_f32(lb[j].outg, (size_t)lb[j].opitch, lb[j].oy, lb[j].coy, 1, 1);
+            if ((r = flush())) return r;
         }
         launch_final(p, s);
     }

@@ -36,3 +36,11 @@ def nl_means(input, patch_size, search_area, sigma, output):
     """apps/nl_means/nl_means_generator.cpp, float32, output has exactly 3 channels."""
     return check(lib.nl_means(input.ptr, ctypes.c_int32(patch_size), ctypes.c_int32(search_area),
                               ctypes.c_float(sigma), output.ptr))
+
+
+def camera_pipe(input, matrix_3200, matrix_7000, color_temp, gamma, contrast, sharpen_strength, blackLevel, whiteLevel,
+                processed):
+    """apps/camera_pipe/camera_pipe_generator.cpp: uint16 Bayer raw -> uint8 RGB."""
+    return check(lib.camera_pipe(input.ptr, matrix_3200.ptr, matrix_7000.ptr, ctypes.c_float(color_temp),
+                                 ctypes.c_float(gamma), ctypes.c_float(contrast), ctypes.c_float(sharpen_strength),
+                                 ctypes.c_int32(blackLevel), ctypes.c_int32(whiteLevel), processed.ptr))

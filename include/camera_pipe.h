@@ -1,0 +1,27 @@
+/* camera_pipe.h — stands in for the header Halide's AOT compiler emits for this filter
+ * (src/CodeGen_C.cpp:1083-1108 argument order: generator inputs in declaration order, then outputs;
+ *  src/CodeGen_C.cpp:675-721 for the _argv and _metadata companions).
+ * Generator: /root/reference/apps/camera_pipe/camera_pipe_generator.cpp:218-238,622
+ * Returns 0 or a negative halide_error_code_t (include/halide_b200_runtime.h).
+ */
+#ifndef HALIDE_B200_CAMERA_PIPE_H
+#define HALIDE_B200_CAMERA_PIPE_H
+
+#include <stdint.h>
+
+struct halide_buffer_t;
+struct halide_filter_metadata_t;
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int camera_pipe(struct halide_buffer_t *input, struct halide_buffer_t *matrix_3200, struct halide_buffer_t *matrix_7000, float color_temp, float gamma, float contrast, float sharpen_strength, int32_t blackLevel, int32_t whiteLevel, struct halide_buffer_t *processed);
+int camera_pipe_argv(void **args);
+const struct halide_filter_metadata_t *camera_pipe_metadata(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* HALIDE_B200_CAMERA_PIPE_H */

@@ -185,6 +185,8 @@ struct halide_filter_metadata_t {
 };
 
 typedef void (*halide_error_handler_t)(void *, const char *);
+typedef void *(*halide_malloc_t)(void *, size_t);
+typedef void (*halide_free_t)(void *, void *);
 
 #endif /* HALIDE_HALIDERUNTIME_H */
 
@@ -194,6 +196,10 @@ typedef void (*halide_error_handler_t)(void *, const char *);
  * src/runtime/posix_error_handler.cpp:9-41).  halide_set_error_handler returns the old handler. */
 void halide_error(void *user_context, const char *msg);
 halide_error_handler_t halide_set_error_handler(halide_error_handler_t handler);
+
+/* Host allocator hooks (HalideRuntime.h; installed by tools/halide_malloc_trace.h in apps/camera_pipe/process.cpp). */
+halide_malloc_t halide_set_custom_malloc(halide_malloc_t user_malloc);
+halide_free_t halide_set_custom_free(halide_free_t user_free);
 
 /* Device bookkeeping (src/runtime/device_interface.cpp:30-56,154-205). */
 int halide_device_malloc(void *user_context, struct halide_buffer_t *buf,

@@ -41,6 +41,16 @@ int oracle_nl_means(const oracle_image_t *in, int patch_size, int search_area, f
 // apps/stencil_chain/stencil_chain_generator.cpp:16-34 (`stencils` is the GeneratorParam, 32 in the app).
 int oracle_stencil_chain(const oracle_image_t *in, const oracle_image_t *out, int stencils);
 
+// apps/camera_pipe/camera_pipe_generator.cpp (whole pipeline).  in: u16 2-D raw; m3200/m7000: f32 (4 x 3); out: u8 3-D.
+// Returns -4 when the input does not cover the stencil footprint.
+int oracle_camera_pipe(const oracle_image_t *in, const oracle_image_t *m3200, const oracle_image_t *m7000, float color_temp,
+                       float gamma, float contrast, float sharpen_strength, int blackLevel, int whiteLevel,
+                       const oracle_image_t *out);
+// The float-derived tables of camera_pipe (Q8.8 matrix [y*4+x], 1024-entry tone curve, sharpen strength x32).
+void oracle_camera_pipe_tables(const float *m3200, const float *m7000, float color_temp, float gamma, float contrast,
+                               float sharpen_strength, int blackLevel, int whiteLevel, int16_t *matrix12, uint8_t *curve1024,
+                               uint8_t *s32_out);
+
 // Primitive probes so the tests can pin the math helpers against known values.
 float oracle_halide_exp(float x);
 float oracle_halide_log(float x);
@@ -52,6 +62,8 @@ int oracle_mod_floor(int a, int b);
 float oracle_ll_remap(int i, float alpha);
 
 int oracle_num_threads(void);
+// torchrun exports OMP_NUM_THREADS=1; the CPU baseline legs of bench.py restore all host cores through this.
+void oracle_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -13,4 +13,5 @@ float oracle_fast_exp(float x) { return hl::fast_exp(x); }
 int oracle_div_floor(int a, int b) { return hl::div_floor(a, b); }
 int oracle_mod_floor(int a, int b) { return hl::mod_floor(a, b); }
 int oracle_num_threads(void) { return omp_get_max_threads(); }
+void oracle_set_num_threads(int n) { omp_set_num_threads(n > 0 ? n : 1); }
 }

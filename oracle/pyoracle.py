@@ -92,6 +92,16 @@ def num_threads():
     return lib().oracle_num_threads()
 
 
+def use_all_cores():
+    """Undo torchrun's OMP_NUM_THREADS=1 for the CPU baseline: one OpenMP thread per available core."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().oracle_set_num_threads(n)
+    return n
+
+
 def ref_blur_available():
     return os.path.exists(_REF_BLUR)
 
@@ -134,4 +144,17 @@ def stencil_chain(inp, out_shape=None, in_mins=None, out_mins=None, stencils=32)
                                    ctypes.c_int(stencils))
     if r != 0:
         raise RuntimeError(f"oracle_stencil_chain returned {r}")
+    return out
+
+
+def camera_pipe(raw, m3200, m7000, color_temp, gamma, contrast, sharpen_strength, black, white, out_shape, in_mins=None,
+                out_mins=None):
+    """raw: uint16 [h, w]; m3200/m7000: float32 [3, 4]; returns uint8 [3, H, W]."""
+    out = np.zeros(out_shape, np.uint8)
+    r = lib().oracle_camera_pipe(ctypes.byref(image(raw, in_mins)), ctypes.byref(image(m3200)), ctypes.byref(image(m7000)),
+                                 ctypes.c_float(color_temp), ctypes.c_float(gamma), ctypes.c_float(contrast),
+                                 ctypes.c_float(sharpen_strength), ctypes.c_int(black), ctypes.c_int(white),
+                                 ctypes.byref(image(out, out_mins)))
+    if r != 0:
+        raise RuntimeError(f"oracle_camera_pipe returned {r}")
     return out

@@ -94,3 +94,14 @@ def test_nl_means_process_cpp(tmp_path, oracle):
     got = _load_halide_npy(tmp_path / "out.npy")
     want = oracle.nl_means(img, 7, 7, 0.12)
     assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-3)) <= 1e-4
+
+
+def test_camera_pipe_process_cpp(tmp_path, oracle):
+    from test_camera_pipe_gpu import M3200, M7000, raw_frame
+    raw = raw_frame(152, 224, 21)
+    _save_halide_npy(tmp_path / "raw.npy", raw)
+    _run([_bin("cp_process"), str(tmp_path / "raw.npy"), "3700", "2.0", "50", "1.0", "3", str(tmp_path / "out.npy")])
+    got = _load_halide_npy(tmp_path / "out.npy")
+    shape = (3, ((152 - 24) // 32) * 32, ((224 - 32) // 32) * 32)
+    want = oracle.camera_pipe(raw, M3200, M7000, 3700.0, 2.0, 50.0, 1.0, 25, 1023, shape)
+    assert np.array_equal(got, want)
