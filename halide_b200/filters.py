@@ -44,3 +44,8 @@ def camera_pipe(input, matrix_3200, matrix_7000, color_temp, gamma, contrast, sh
     return check(lib.camera_pipe(input.ptr, matrix_3200.ptr, matrix_7000.ptr, ctypes.c_float(color_temp),
                                  ctypes.c_float(gamma), ctypes.c_float(contrast), ctypes.c_float(sharpen_strength),
                                  ctypes.c_int32(blackLevel), ctypes.c_int32(whiteLevel), processed.ptr))
+
+
+def conv_layer(input, filter, bias, relu):
+    """apps/conv_layer/conv_layer_generator.cpp: 3x3 conv + bias + relu, fixed shapes (N5 CI128 CO128 100x80), f32."""
+    return check(lib.conv_layer(input.ptr, filter.ptr, bias.ptr, relu.ptr))

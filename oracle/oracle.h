@@ -51,6 +51,9 @@ void oracle_camera_pipe_tables(const float *m3200, const float *m7000, float col
                                float sharpen_strength, int blackLevel, int whiteLevel, int16_t *matrix12, uint8_t *curve1024,
                                uint8_t *s32_out);
 
+// apps/conv_layer/conv_layer_generator.cpp:17-27; dense arrays in the generator's fixed layouts.
+int oracle_conv_layer(const float *input, const float *filter, const float *bias, float *out, int N, int CI, int CO, int W, int H);
+
 // Primitive probes so the tests can pin the math helpers against known values.
 float oracle_halide_exp(float x);
 float oracle_halide_log(float x);

@@ -158,3 +158,15 @@ def camera_pipe(raw, m3200, m7000, color_temp, gamma, contrast, sharpen_strength
     if r != 0:
         raise RuntimeError(f"oracle_camera_pipe returned {r}")
     return out
+
+
+def conv_layer(inp, filt, bias):
+    """inp: float32 [N, H+2, W+2, CI]; filt: [CI, 3, 3, CO]; bias: [CO] -> float32 [N, H, W, CO]."""
+    n, hp, wp, ci = inp.shape
+    co = bias.shape[0]
+    out = np.zeros((n, hp - 2, wp - 2, co), np.float32)
+    inp, filt, bias = (np.ascontiguousarray(a, np.float32) for a in (inp, filt, bias))
+    f = ctypes.c_void_p
+    lib().oracle_conv_layer(inp.ctypes.data_as(f), filt.ctypes.data_as(f), bias.ctypes.data_as(f), out.ctypes.data_as(f), n, ci, co,
+                            wp - 2, hp - 2)
+    return out

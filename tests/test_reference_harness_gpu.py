@@ -105,3 +105,8 @@ def test_camera_pipe_process_cpp(tmp_path, oracle):
     shape = (3, ((152 - 24) // 32) * 32, ((224 - 32) // 32) * 32)
     want = oracle.camera_pipe(raw, M3200, M7000, 3700.0, 2.0, 50.0, 1.0, 25, 1023, shape)
     assert np.array_equal(got, want)
+
+
+def test_conv_layer_process_cpp():
+    out = _run([_bin("conv_process")])
+    assert "Manually-tuned time" in out and "Auto-scheduled time" in out
