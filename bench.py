@@ -119,14 +119,32 @@ def recorded_traffic(workload):
         return None
 
 
+def best_thread_count(img, candidates=None):
+    """The oracle's OpenMP scaling flattens on very wide hosts (many small parallel regions over the coarse
+    pyramid levels): time one frame at a few thread counts and keep the fastest — 'all the host threads it can use'."""
+    from oracle import pyoracle
+    ncores = pyoracle.use_all_cores()
+    cands = sorted({c for c in (candidates or [8, 16, 32, 64, ncores]) if c <= ncores} | {min(ncores, 8)})
+    best_n, best_t = cands[0], float("inf")
+    for n in cands:
+        pyoracle.set_threads(n)
+        pyoracle.local_laplacian(img, LEVELS, ALPHA, BETA)
+        t0 = time.perf_counter()
+        pyoracle.local_laplacian(img, LEVELS, ALPHA, BETA)
+        t = time.perf_counter() - t0
+        if t < best_t:
+            best_n, best_t = n, t
+    pyoracle.set_threads(best_n)
+    return best_n
+
+
 def cpu_oracle_rate(W, H, budget_s=12.0, max_steps=8):
     """Time the CPU oracle on full frames of the workload (bounded sample)."""
     import numpy as np
     from oracle import pyoracle
-    pyoracle.use_all_cores()
     rng = np.random.default_rng(0)
     img = rng.integers(0, 65536, (3, H, W), dtype=np.uint16)
-    pyoracle.local_laplacian(img, LEVELS, ALPHA, BETA)  # warm-up (page faults, thread pool)
+    threads = best_thread_count(img)
     times = []
     t_all = time.perf_counter()
     while len(times) < max_steps and time.perf_counter() - t_all < budget_s:
@@ -134,8 +152,9 @@ def cpu_oracle_rate(W, H, budget_s=12.0, max_steps=8):
         pyoracle.local_laplacian(img, LEVELS, ALPHA, BETA)
         times.append(time.perf_counter() - t0)
     best = min(times)
-    return {"value": W * H / 1e6 / best, "unit": "Mpixels/s", "cores": pyoracle.num_threads(), "kind": "port",
-            "sample": f"{len(times)} full {W}x{H}x3 frames, best of; oracle/oracle_local_laplacian.cpp -O2 OpenMP",
+    return {"value": W * H / 1e6 / best, "unit": "Mpixels/s", "cores": threads, "kind": "port",
+            "sample": f"{len(times)} full {W}x{H}x3 frames, best of; oracle/oracle_local_laplacian.cpp -O2 OpenMP, "
+                      f"{threads} threads (fastest of a sweep up to all host cores)",
             "ms": best * 1e3}
 
 
@@ -145,7 +164,6 @@ def run_reference(args, rank, world):
         return
     import numpy as np
     from oracle import pyoracle
-    pyoracle.use_all_cores()
     W, H = WORKLOADS[args.workload]
     # bounded sample: a band of rows such that the whole run stays within a few minutes
     rows = H
@@ -154,6 +172,7 @@ def run_reference(args, rank, world):
         rows //= 2
     rng = np.random.default_rng(0)
     img = rng.integers(0, 65536, (3, rows, W), dtype=np.uint16)
+    threads = best_thread_count(img)
     for _ in range(max(1, args.warmup)):
         pyoracle.local_laplacian(img, LEVELS, ALPHA, BETA)
     t0 = time.perf_counter()
@@ -167,8 +186,8 @@ def run_reference(args, rank, world):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 internal, u16 I/O",
             "data": "synthetic", "config": {"workload": args.workload, "levels": LEVELS, "alpha": 1, "beta": 1,
                                             "frame": [W, H, 3]},
-            "cpu_baseline": {"value": val, "unit": "Mpixels/s", "cores": pyoracle.num_threads(), "kind": "port",
-                             "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "Mpixels/s", "cores": threads, "kind": "port",
+                             "sample": sample + f"; {threads} OpenMP threads (fastest of a sweep up to all host cores)"},
             "e2e": {"value": val, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)

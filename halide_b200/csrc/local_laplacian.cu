@@ -144,16 +144,27 @@ int alloc_levels(Plan &p, hb::Scratch &scratch) {
 const dim3 kBlk(32, 8);
 dim3 grid_for(int w, int h) { return dim3((w + 31) / 32, (h + 7) / 8); }
 
-int strip_rows(const LevelBuf &d) {
-    // tall strips amortise the 2-row apron; shrink them when the level is too small to fill 148 SMs
-    int rows = 16;
-    int sx = (d.sx.n() + kStripCols - 1) / kStripCols;
-    while (rows > 2 && (int64_t)((sx + 3) / 4) * ((d.cy.n() + rows - 1) / rows) < 148 * 4) rows >>= 1;
-    return rows;
+// Strip kernels run with one block per resident slot and a balanced static partition of the level's rows
+// (ll_down_strip_kernel), so there is no tail wave.
+template<typename Kern>
+int strip_slots(Kern kern, size_t smem) {
+    int dev = 0, sms = 148, per_sm = 8;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 4;
+    }
+    return sms * per_sm;
 }
-dim3 strip_grid(const LevelBuf &d, int rows) {
-    int sx = (d.sx.n() + kStripCols - 1) / kStripCols;
-    return dim3((sx + 3) / 4, (d.cy.n() + rows - 1) / rows);
+int strip_xblocks(const LevelBuf &d) {
+    return ((d.sx.n() + kStripCols - 1) / kStripCols + 3) / 4;
+}
+int strip_grid(const LevelBuf &d, int slots) {
+    // never more blocks than block-rows of work; at least 2 destination rows per block where possible
+    long long work = (long long)strip_xblocks(d) * d.cy.n();
+    long long g = work / 2 < 1 ? 1 : work / 2;
+    return (int)(g < slots ? g : slots);
 }
 
 void launch_lut(Plan &p, cudaStream_t s) {
@@ -166,17 +177,24 @@ void launch_down(Plan &p, int j, cudaStream_t s) {  // produce level j (j >= 1) 
     const bool fast = (p.K == 8) && !(g_force_naive & 1);
     if (j == 1) {
         if (fast) {
-            int rows = strip_rows(lb[1]);
             size_t smem = (size_t)(2 * p.f.lut_half + 1) * sizeof(float);
-            HB_LAUNCH("ll_level1_strip", (ll_down_strip_kernel<8, true>), strip_grid(lb[1], rows), 128, smem, s, p.f, lb[1],
-                      lb[1], rows);
+            const int xb = strip_xblocks(lb[1]);
+            if (p.f.halo_top_rows || p.f.halo_bot_rows || p.f.clamp_y0 != p.f.in_y0 || p.f.clamp_h != p.f.in_h) {
+                static int slots = strip_slots(ll_down_strip_kernel<8, true, true>, 16 * 1024);
+                HB_LAUNCH("ll_level1_strip", (ll_down_strip_kernel<8, true, true>), strip_grid(lb[1], slots), 128, smem, s, p.f,
+                          lb[1], lb[1], xb);
+            } else {
+                static int slots = strip_slots(ll_down_strip_kernel<8, true, false>, 16 * 1024);
+                HB_LAUNCH("ll_level1_strip", (ll_down_strip_kernel<8, true, false>), strip_grid(lb[1], slots), 128, smem, s, p.f,
+                          lb[1], lb[1], xb);
+            }
         } else {
             HB_LAUNCH("ll_level1", ll_level1_naive_kernel, grid_for(lb[1].sx.n(), lb[1].cy.n()), kBlk, 0, s, p.f, lb[1]);
         }
     } else if (fast) {
-        int rows = strip_rows(lb[j]);
-        HB_LAUNCH("ll_down_strip", (ll_down_strip_kernel<8, false>), strip_grid(lb[j], rows), 128, 0, s, p.f, lb[j - 1], lb[j],
-                  rows);
+        static int slots = strip_slots(ll_down_strip_kernel<8, false, false>, 0);
+        HB_LAUNCH("ll_down_strip", (ll_down_strip_kernel<8, false, false>), strip_grid(lb[j], slots), 128, 0, s, p.f, lb[j - 1],
+                  lb[j], strip_xblocks(lb[j]));
     } else {
         HB_LAUNCH("ll_down", ll_down_naive_kernel, grid_for(lb[j].sx.n(), lb[j].cy.n()), kBlk, 0, s, lb[j - 1], lb[j], p.K);
     }

@@ -102,6 +102,10 @@ def use_all_cores():
     return n
 
 
+def set_threads(n):
+    lib().oracle_set_num_threads(int(n))
+
+
 def ref_blur_available():
     return os.path.exists(_REF_BLUR)
 
