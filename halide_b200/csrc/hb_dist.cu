@@ -27,6 +27,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -48,6 +49,7 @@ int load_nccl() {
     HB_SYM(CommDestroy, "ncclCommDestroy")
     HB_SYM(Send, "ncclSend")
     HB_SYM(Recv, "ncclRecv")
+    HB_SYM(AllGather, "ncclAllGather")
     HB_SYM(GroupStart, "ncclGroupStart")
     HB_SYM(GroupEnd, "ncclGroupEnd")
     HB_SYM(GetErrorString, "ncclGetErrorString")
@@ -85,6 +87,86 @@ int exchange(const Msg *msgs, int n, cudaStream_t s) {
         }
     }
     return check(g_nccl.GroupEnd(), "ncclGroupEnd");
+}
+
+int allgather_bytes(const void *send, void *recv_all, size_t bytes) {
+    if (!active()) return hb::fail(halide_error_code_generic_error, "dist: all-gather without an initialised communicator");
+    void *dsend = nullptr, *drecv = nullptr;
+    cudaStream_t s = hb::stream();
+    if (cudaMalloc(&dsend, bytes) != cudaSuccess || cudaMalloc(&drecv, bytes * g_size) != cudaSuccess) {
+        cudaGetLastError();
+        return hb::fail(halide_error_code_device_malloc_failed, "dist: all-gather staging allocation failed");
+    }
+    cudaMemcpyAsync(dsend, send, bytes, cudaMemcpyHostToDevice, s);
+    int r = check(g_nccl.AllGather(dsend, drecv, bytes, ncclInt8, g_comm, s), "ncclAllGather");
+    if (!r) {
+        cudaMemcpyAsync(recv_all, drecv, bytes * g_size, cudaMemcpyDeviceToHost, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess) r = hb::fail(halide_error_code_generic_error, "dist: all-gather failed");
+    }
+    cudaFree(dsend);
+    cudaFree(drecv);
+    return r;
+}
+
+namespace {
+
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256) peer_exchange_kernel(PeerXchg x) {
+    // 1. push: grid-stride copy of every segment into the neighbour's memory (16-byte or 2-byte elements)
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int i = 0; i < x.nseg; i++) {
+        const PeerSeg &g = x.seg[i];
+        if (g.elem == 16) {
+            const uint4 *s = reinterpret_cast<const uint4 *>(g.src);
+            uint4 *d = reinterpret_cast<uint4 *>(g.dst);
+            for (unsigned k = tid; k < g.bytes / 16; k += nth) d[k] = s[k];
+        } else {
+            const unsigned short *s = reinterpret_cast<const unsigned short *>(g.src);
+            unsigned short *d = reinterpret_cast<unsigned short *>(g.dst);
+            for (unsigned k = tid; k < g.bytes / 2; k += nth) d[k] = s[k];
+        }
+    }
+    // 2. announce: the last block to finish its slice releases the flags in the neighbours' memory
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned prev = atomicAdd(x.done_counter, 1u);
+        if (prev == gridDim.x - 1) {
+            *x.done_counter = 0u;
+            __threadfence_system();
+            if (x.peer_flag[0]) st_release_sys(x.peer_flag[0], x.epoch);
+            if (x.peer_flag[1]) st_release_sys(x.peer_flag[1], x.epoch);
+        }
+    }
+    // 3. wait for the neighbours' rows of this step (block 0 only; bounded spin so a protocol bug cannot hang the GPU)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int d = 0; d < 2; d++) {
+            if (!x.my_flag[d]) continue;
+            long long t0 = clock64();
+            while ((int)(ld_acquire_sys(x.my_flag[d]) - x.epoch) < 0) {  // epochs only grow
+                if (clock64() - t0 > 4000000000LL) {  // ~2 s
+                    *x.error_flag = 1u;
+                    break;
+                }
+                __nanosleep(100);
+            }
+        }
+        __threadfence_system();
+    }
+}
+
+}  // namespace
+
+void launch_peer_exchange(const PeerXchg &x, cudaStream_t s) {
+    HB_LAUNCH("peer_exchange", peer_exchange_kernel, 8, 256, 0, s, x);
 }
 
 }  // namespace hbdist

@@ -18,4 +18,29 @@ int size();
 // One ncclGroup of point-to-point messages enqueued on stream `s` (ordered with the kernels on it).
 int exchange(const Msg *msgs, int n, cudaStream_t s);
 
+// Host-side all-gather of a small POD blob (plan setup only, synchronous): recv_all holds size() blobs in rank order.
+int allgather_bytes(const void *send, void *recv_all, size_t bytes_per_rank);
+
+// ---- peer-memory halo exchange (NVLink stores + flags instead of ncclSend/ncclRecv) ------------------------
+// One kernel per exchange step: every block copies a slice of this rank's boundary rows straight into the
+// neighbours' halo rows (peer pointers obtained through CUDA IPC), the last block to finish releases a flag in the
+// neighbour's memory, and one thread then spins (acquire, with a timeout) until both neighbours' flags for this
+// step and epoch have arrived.  Stream order makes the halo rows visible to the next kernel.
+struct PeerSeg {
+    const void *src;  // local rows
+    void *dst;        // same rows in the neighbour's buffer (peer address)
+    unsigned bytes;
+    unsigned elem;    // copy granularity in bytes: 16 or 2
+};
+struct PeerXchg {
+    PeerSeg seg[12];
+    int nseg;
+    unsigned *peer_flag[2];      // where to announce completion: [0] up neighbour, [1] down neighbour (null if none)
+    const unsigned *my_flag[2];  // where the neighbours announce theirs
+    unsigned epoch;
+    unsigned *done_counter;      // local scratch counter (self-resetting)
+    unsigned *error_flag;        // set to 1 on wait timeout
+};
+void launch_peer_exchange(const PeerXchg &x, cudaStream_t s);
+
 }  // namespace hbdist

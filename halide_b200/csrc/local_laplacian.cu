@@ -13,6 +13,11 @@
 // gray / gPyramid[0] / lPyramid / outLPyramid / outGPyramid[0] are never materialised: they are
 // recomputed from the uint16 input where needed (8 f32 planes at full resolution would be
 // 32 B/px of traffic against 12 B/px of compulsory I/O).
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
 #include "hb_dist.h"
 #include "ll_kernels.cuh"
 
@@ -291,6 +296,121 @@ int run_local_laplacian(halide_buffer_t *input, int levels, float alpha, float b
     return 0;
 }
 
+// ---- peer-memory plan for the row-sharded variant ---------------------------------------------------------
+// All level buffers of a rank live in one cudaMalloc'ed slab whose CUDA-IPC handle and internal layout are
+// all-gathered once per geometry; afterwards every halo exchange is one kernel that stores this rank's boundary rows
+// straight into the neighbours' slabs over NVLink and handshakes through flags (hb_dist.h: PeerXchg).
+struct SlabLayout {  // POD, exchanged between ranks
+    unsigned long long gp[ll::kMaxJ], ing[ll::kMaxJ], outg[ll::kMaxJ], halo_top, halo_bot, flags, lut, total;
+    int sy_lo[ll::kMaxJ], oy_lo[ll::kMaxJ];
+    int halo_top_rows, halo_bot_rows;
+    cudaIpcMemHandle_t handle;
+};
+struct ShardPlan {
+    int key[10];
+    bool valid = false;
+    char *slab = nullptr;
+    SlabLayout mine, up, dn;
+    char *up_base = nullptr, *dn_base = nullptr;
+    unsigned epoch = 0;
+    unsigned *host_error = nullptr, *dev_error = nullptr;  // mapped pinned: set by a timed-out wait
+};
+ShardPlan g_shard;
+
+void destroy_shard_plan() {
+    if (!g_shard.valid) return;
+    cudaDeviceSynchronize();
+    if (g_shard.up_base) cudaIpcCloseMemHandle(g_shard.up_base);
+    if (g_shard.dn_base) cudaIpcCloseMemHandle(g_shard.dn_base);
+    if (g_shard.slab) cudaFree(g_shard.slab);
+    if (g_shard.host_error) cudaFreeHost(g_shard.host_error);
+    g_shard = ShardPlan();
+}
+
+// Collective: every rank must call it with its own geometry at the same point of the program.
+int build_shard_plan(const Plan &p, const int *key, bool first, bool last) {
+    destroy_shard_plan();
+    ShardPlan &sp = g_shard;
+    SlabLayout &L = sp.mine;
+    memset(&L, 0, sizeof(L));
+    unsigned long long off = 0;
+    auto take = [&](unsigned long long bytes) {
+        unsigned long long o = off;
+        off += (bytes + 255) & ~255ull;
+        return o;
+    };
+    L.flags = take(256);  // [step*2 + dir] epochs, then the done counter at word 48
+    L.lut = take((2ull * p.f.lut_half + 1) * sizeof(float));
+    L.halo_top_rows = first ? 0 : 1;
+    L.halo_bot_rows = last ? 0 : 2;
+    L.halo_top = take((unsigned long long)p.f.in_c * 1 * p.f.in_w * sizeof(uint16_t));
+    L.halo_bot = take((unsigned long long)p.f.in_c * 2 * p.f.in_w * sizeof(uint16_t));
+    for (int j = 1; j < p.J; j++) {
+        const ll::Level &lv = p.geom.lv[j];
+        unsigned long long gpix = (unsigned long long)lv.sy.n() * lv.gpitch;
+        L.gp[j] = take(gpix * p.K * sizeof(float));
+        L.ing[j] = take(gpix * sizeof(float));
+        L.outg[j] = take((unsigned long long)lv.oy.n() * lv.opitch * sizeof(float));
+        L.sy_lo[j] = lv.sy.lo;
+        L.oy_lo[j] = lv.oy.lo;
+    }
+    L.total = off;
+    if (cudaMalloc((void **)&sp.slab, L.total) != cudaSuccess) {
+        cudaGetLastError();
+        return hb::fail(halide_error_code_device_malloc_failed, "local_laplacian_sharded: slab allocation of %llu bytes failed", L.total);
+    }
+    cudaMemset(sp.slab + L.flags, 0, 256);
+    if (cudaIpcGetMemHandle(&L.handle, sp.slab) != cudaSuccess) {
+        cudaGetLastError();
+        return hb::fail(halide_error_code_generic_error, "local_laplacian_sharded: cudaIpcGetMemHandle failed");
+    }
+    if (cudaHostAlloc((void **)&sp.host_error, sizeof(unsigned), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void **)&sp.dev_error, sp.host_error, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return hb::fail(halide_error_code_generic_error, "local_laplacian_sharded: mapped error flag allocation failed");
+    }
+    *sp.host_error = 0;
+    cudaDeviceSynchronize();
+    const int n = hbdist::size(), me = hbdist::rank();
+    std::vector<SlabLayout> all(n);
+    int r = hbdist::allgather_bytes(&L, all.data(), sizeof(SlabLayout));
+    if (r) return r;
+    if (!first) {
+        sp.up = all[me - 1];
+        if (cudaIpcOpenMemHandle((void **)&sp.up_base, sp.up.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            return hb::fail(halide_error_code_generic_error, "local_laplacian_sharded: cannot map rank %d's slab (no peer access?)", me - 1);
+        }
+    }
+    if (!last) {
+        sp.dn = all[me + 1];
+        if (cudaIpcOpenMemHandle((void **)&sp.dn_base, sp.dn.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            return hb::fail(halide_error_code_generic_error, "local_laplacian_sharded: cannot map rank %d's slab (no peer access?)", me + 1);
+        }
+    }
+    memcpy(sp.key, key, sizeof(sp.key));
+    sp.valid = true;
+    return 0;
+}
+
+void bind_slab(Plan &p) {  // point the plan's buffers into the slab
+    const ShardPlan &sp = g_shard;
+    p.lut = (float *)(sp.slab + sp.mine.lut);
+    p.f.lut = p.lut;
+    for (int j = 1; j < p.J; j++) {
+        const ll::Level &lv = p.geom.lv[j];
+        LevelBuf &b = p.ls.lv[j];
+        b.sx = lv.sx; b.sy = lv.sy; b.ox = lv.ox; b.oy = lv.oy;
+        b.cy = lv.cy; b.coy = lv.coy; b.gy = lv.gy;
+        b.gpitch = lv.gpitch; b.opitch = lv.opitch;
+        b.gp = (float *)(sp.slab + sp.mine.gp[j]);
+        b.ing = (float *)(sp.slab + sp.mine.ing[j]);
+        b.outg = (float *)(sp.slab + sp.mine.outg[j]);
+    }
+    p.ls.lv[0] = p.ls.lv[1];
+}
+
 // ---- row-sharded variant (one process per GPU) -----------------------------------------------------------
 // `input`/`output` describe this rank's band: all columns and channels of the frame, rows
 // [dim[1].min, dim[1].min + extent) in the frame's coordinates.  frame_y_min/extent give the rows of the whole
@@ -342,10 +462,102 @@ int run_local_laplacian_sharded(halide_buffer_t *input, int levels, float alpha,
     p.geom = ll::make_band_geom(whole, bl);
     p.f.clamp_y0 = frame_y.lo;
     p.f.clamp_h = frame_y.n();
+    static const bool use_peer = [] {
+        const char *e = getenv("HALIDE_B200_HALO");
+        return !(e && strcmp(e, "nccl") == 0);
+    }();
+    cudaStream_t s = hb::stream();
+    const int up = rank - 1, dn = rank + 1;
+    const int C = p.f.in_c;
+    if (use_peer) {
+        // ---- peer-memory path: slab + IPC plan (built collectively on first use / geometry change) ----
+        const int key[10] = {W, p.f.in_w, band.lo, band.hi, frame_y.lo, frame_y.hi, rank, nranks, C, (int)(p.f.in_sy & 0x7fffffff)};
+        if (!g_shard.valid || memcmp(g_shard.key, key, sizeof(key)) != 0) {
+            if ((r = build_shard_plan(p, key, first, last))) return r;
+        }
+        ShardPlan &sp = g_shard;
+        if (*sp.host_error) {
+            return hb::fail(halide_error_code_device_run_failed, "local_laplacian_sharded: a previous halo wait timed out (neighbour rank stalled?)");
+        }
+        bind_slab(p);
+        p.f.halo_pitch = p.f.in_w;
+        p.f.halo_top = (const uint16_t *)(sp.slab + sp.mine.halo_top);
+        p.f.halo_bot = (const uint16_t *)(sp.slab + sp.mine.halo_bot);
+        p.f.halo_top_rows = sp.mine.halo_top_rows;
+        p.f.halo_bot_rows = sp.mine.halo_bot_rows;
+        sp.epoch++;
+        unsigned *flags = (unsigned *)(sp.slab + sp.mine.flags);
+        int step = 0;
+        hbdist::PeerXchg x;
+        auto begin_step = [&]() {
+            memset(&x, 0, sizeof(x));
+            x.epoch = sp.epoch;
+            x.done_counter = flags + 48;
+            x.error_flag = sp.dev_error;
+            // I am the DOWN neighbour of rank-1 (its slot dir 1) and the UP neighbour of rank+1 (its slot dir 0)
+            x.peer_flag[0] = first ? nullptr : (unsigned *)(sp.up_base + sp.up.flags) + step * 2 + 1;
+            x.peer_flag[1] = last ? nullptr : (unsigned *)(sp.dn_base + sp.dn.flags) + step * 2 + 0;
+            x.my_flag[0] = first ? nullptr : flags + step * 2 + 0;
+            x.my_flag[1] = last ? nullptr : flags + step * 2 + 1;
+        };
+        auto add_seg = [&](const void *src, void *dst, size_t bytes, unsigned elem) {
+            x.seg[x.nseg].src = src; x.seg[x.nseg].dst = dst;
+            x.seg[x.nseg].bytes = (unsigned)bytes; x.seg[x.nseg].elem = elem;
+            x.nseg++;
+        };
+        auto end_step = [&]() {
+            hbdist::launch_peer_exchange(x, s);
+            step++;
+        };
+        // rows of a row-major f32 array: my first n_up owned rows go up, my last owned row goes down
+        auto rows_f32 = [&](const float *mine, const unsigned long long *peer_off_up, const unsigned long long *peer_off_dn, int j,
+                            size_t row_elems, int my_lo, int own_lo, int own_hi, int up_lo, int dn_lo, int n_up) {
+            const size_t rb = row_elems * sizeof(float);
+            if (!first) add_seg(mine + (size_t)(own_lo - my_lo) * row_elems, sp.up_base + peer_off_up[j] + (size_t)(own_lo - up_lo) * rb, n_up * rb, 16);
+            if (!last) add_seg(mine + (size_t)(own_hi - my_lo) * row_elems, sp.dn_base + peer_off_dn[j] + (size_t)(own_hi - dn_lo) * rb, rb, 16);
+        };
+        {
+            hb::CallTimer timer(s);
+            // step 0: input rows (per channel; rows may be strided in the caller's buffer -> one segment per row)
+            begin_step();
+            const size_t rb = (size_t)p.f.in_w * sizeof(uint16_t);
+            for (int c = 0; c < C; c++) {
+                const uint16_t *plane = (const uint16_t *)din + (int64_t)c * p.f.in_sc;
+                if (!first) {  // my rows 0,1 are the up neighbour's two bottom-halo rows
+                    char *dst = sp.up_base + sp.up.halo_bot + (size_t)c * 2 * rb;
+                    add_seg(plane, dst, rb, 2);
+                    add_seg(plane + p.f.in_sy, dst + rb, rb, 2);
+                }
+                if (!last) {  // my last row is the down neighbour's top-halo row
+                    add_seg(plane + (int64_t)(p.f.in_h - 1) * p.f.in_sy, sp.dn_base + sp.dn.halo_top + (size_t)c * rb, rb, 2);
+                }
+            }
+            end_step();
+            launch_lut(p, s);
+            LevelBuf *lb = p.ls.lv;
+            for (int j = 1; j < p.J; j++) {
+                launch_down(p, j, s);
+                begin_step();
+                rows_f32(lb[j].gp, sp.up.gp, sp.dn.gp, j, (size_t)lb[j].gpitch * p.K, lb[j].sy.lo, lb[j].cy.lo, lb[j].cy.hi,
+                         sp.up.sy_lo[j], sp.dn.sy_lo[j], 2);
+                rows_f32(lb[j].ing, sp.up.ing, sp.dn.ing, j, (size_t)lb[j].gpitch, lb[j].sy.lo, lb[j].cy.lo, lb[j].cy.hi,
+                         sp.up.sy_lo[j], sp.dn.sy_lo[j], 2);
+                end_step();
+            }
+            for (int j = p.J - 1; j >= 1; j--) {
+                launch_up(p, j, s);
+                begin_step();
+                rows_f32(lb[j].outg, sp.up.outg, sp.dn.outg, j, (size_t)lb[j].opitch, lb[j].oy.lo, lb[j].coy.lo, lb[j].coy.hi,
+                         sp.up.oy_lo[j], sp.dn.oy_lo[j], 1);
+                end_step();
+            }
+            launch_final(p, s);
+        }
+    } else {
     hb::Scratch scratch;
     if ((r = alloc_levels(p, scratch))) return r;
     // input halo: 1 row above, 2 rows below (the 1-3-3-1 taps of level 1), per channel, x relative to in_x0
-    const int ht = first ? 0 : 1, hbn = last ? 0 : 2, C = p.f.in_c;
+    const int ht = first ? 0 : 1, hbn = last ? 0 : 2;
     uint16_t *halo_top = nullptr, *halo_bot = nullptr;
     p.f.halo_pitch = p.f.in_w;
     if (ht) halo_top = scratch.get<uint16_t>((size_t)C * ht * p.f.in_w);
@@ -356,9 +568,7 @@ int run_local_laplacian_sharded(halide_buffer_t *input, int levels, float alpha,
     p.f.halo_top = halo_top; p.f.halo_bot = halo_bot;
     p.f.halo_top_rows = ht; p.f.halo_bot_rows = hbn;
 
-    cudaStream_t s = hb::stream();
     hbdist::Msg msgs[64];
-    const int up = rank - 1, dn = rank + 1;
     // queue the halo messages of one row-major f32 array: my first n_up owned rows go up and my last owned row goes
     // down; one row arrives above and n_dn_recv rows arrive below
     int nq = 0;
@@ -417,6 +627,7 @@ int run_local_laplacian_sharded(halide_buffer_t *input, int levels, float alpha,
         }
         launch_final(p, s);
     }
+    }  // NCCL path
     if ((r = hb::check_cuda(cudaGetLastError(), "local_laplacian_sharded launch", halide_error_code_device_run_failed))) return r;
     hb::mark_output_written(output);
     return 0;
