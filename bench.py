@@ -261,7 +261,12 @@ def run_ours(args, rank, world, local_rank):
 
     # keep the GPU busy a little longer so the clock sampler has samples even for short runs
     # (a fixed step count: under sharding every rank must issue the same number of exchanges)
-    if len(sampler.samples) < 5:
+    need_more = len(sampler.samples) < 5
+    if dist is not None:  # the decision must be collective: every rank issues the same number of exchanges
+        tt = torch.tensor([1 if need_more else 0], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        need_more = bool(tt.item())
+    if need_more:
         sampler.start()
         for i in range(300):
             step(i)
