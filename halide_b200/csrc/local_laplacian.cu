@@ -102,6 +102,7 @@ int check_and_query(halide_buffer_t *input, int levels, halide_buffer_t *output,
 void fill_frame(Plan &p, halide_buffer_t *input, halide_buffer_t *output, void *din, void *dout, int levels, float alpha,
                 float beta) {
     LLFrame &f = p.f;
+    memset(&f.io, 0, sizeof(f.io));
     f.in = (const uint16_t *)din;
     f.in_sy = input->dim[1].stride; f.in_sc = input->dim[2].stride;
     f.in_x0 = input->dim[0].min; f.in_y0 = input->dim[1].min; f.in_c0 = input->dim[2].min;
@@ -197,9 +198,16 @@ void launch_down(Plan &p, int j, cudaStream_t s) {  // produce level j (j >= 1) 
             HB_LAUNCH("ll_level1", ll_level1_naive_kernel, grid_for(lb[1].sx.n(), lb[1].cy.n()), kBlk, 0, s, p.f, lb[1]);
         }
     } else if (fast) {
-        static int slots = strip_slots(ll_down_strip_kernel<8, false, false>, 0);
-        HB_LAUNCH("ll_down_strip", (ll_down_strip_kernel<8, false, false>), strip_grid(lb[j], slots), 128, 0, s, p.f, lb[j - 1],
-                  lb[j], strip_xblocks(lb[j]));
+        const bool peer = p.f.io.up_flag || p.f.io.dn_flag || p.f.io.wait_up[0] || p.f.io.wait_dn[0];
+        if (peer) {
+            static int slots = strip_slots(ll_down_strip_kernel<8, false, true>, 0);
+            HB_LAUNCH("ll_down_strip", (ll_down_strip_kernel<8, false, true>), strip_grid(lb[j], slots), 128, 0, s, p.f, lb[j - 1],
+                      lb[j], strip_xblocks(lb[j]));
+        } else {
+            static int slots = strip_slots(ll_down_strip_kernel<8, false, false>, 0);
+            HB_LAUNCH("ll_down_strip", (ll_down_strip_kernel<8, false, false>), strip_grid(lb[j], slots), 128, 0, s, p.f, lb[j - 1],
+                      lb[j], strip_xblocks(lb[j]));
+        }
     } else {
         HB_LAUNCH("ll_down", ll_down_naive_kernel, grid_for(lb[j].sx.n(), lb[j].cy.n()), kBlk, 0, s, lb[j - 1], lb[j], p.K);
     }
@@ -211,10 +219,14 @@ void launch_up(Plan &p, int j, cudaStream_t s) {  // produce outGPyramid[j] (1 <
     const bool fast_up = (p.K == 8) && !(g_force_naive & 2);
     if (fast_up && j < p.J - 1) {
         dim3 g((lb[j].ox.n() + kUpTW - 1) / kUpTW, (lb[j].coy.n() + kUpTH - 1) / kUpTH);
-        HB_LAUNCH("ll_up_tile", (ll_up_tile_kernel<false>), g, 256, 0, s, p.f, lb[j], lb[j + 1]);
+        if (p.f.io.up_flag || p.f.io.dn_flag || p.f.io.wait_up[0] || p.f.io.wait_dn[0]) {
+            HB_LAUNCH("ll_up_tile", (ll_up_tile_kernel<false, true>), g, 256, 0, s, p.f, lb[j], lb[j + 1]);
+        } else {
+            HB_LAUNCH("ll_up_tile", (ll_up_tile_kernel<false, false>), g, 256, 0, s, p.f, lb[j], lb[j + 1]);
+        }
     } else {
         HB_LAUNCH("ll_up", ll_up_naive_kernel, grid_for(lb[j].ox.n(), lb[j].coy.n()), kBlk, 0, s, lb[j],
-                  lb[j == p.J - 1 ? j : j + 1], p.K, p.f.flm1, p.f.levels, j == p.J - 1 ? 1 : 0);
+                  lb[j == p.J - 1 ? j : j + 1], p.K, p.f.flm1, p.f.levels, j == p.J - 1 ? 1 : 0, p.f.io);
     }
 }
 
@@ -223,7 +235,11 @@ void launch_final(Plan &p, cudaStream_t s) {
     if (p.J > 1 && p.K == 8 && !(g_force_naive & 4) && p.f.C <= 3) {
         dim3 g((p.f.W + kUpTW - 1) / kUpTW, (p.f.H + kUpTH - 1) / kUpTH);
         size_t smem = 513 * sizeof(float);
-        HB_LAUNCH("ll_final_tile", (ll_up_tile_kernel<true>), g, 256, smem, s, p.f, lb[1], lb[1]);
+        if (p.f.io.wait_up[0] || p.f.io.wait_dn[0]) {
+            HB_LAUNCH("ll_final_tile", (ll_up_tile_kernel<true, true>), g, 256, smem, s, p.f, lb[1], lb[1]);
+        } else {
+            HB_LAUNCH("ll_final_tile", (ll_up_tile_kernel<true, false>), g, 256, smem, s, p.f, lb[1], lb[1]);
+        }
     } else {
         HB_LAUNCH("ll_final", ll_final_naive_kernel, grid_for(p.f.W, p.f.H), kBlk, 0, s, p.f, lb[1], p.J > 1 ? 1 : 0);
     }
@@ -532,26 +548,64 @@ int run_local_laplacian_sharded(halide_buffer_t *input, int levels, float alpha,
                     add_seg(plane + (int64_t)(p.f.in_h - 1) * p.f.in_sy, sp.dn_base + sp.dn.halo_top + (size_t)c * rb, rb, 2);
                 }
             }
+            // push only: the level-1 kernel's boundary blocks acquire the step-0 flags themselves (PeerIO)
+            x.my_flag[0] = x.my_flag[1] = nullptr;
             end_step();
             launch_lut(p, s);
             LevelBuf *lb = p.ls.lv;
+            // From here on there are no exchange kernels: producers mirror their boundary rows into the neighbours'
+            // slabs and release the step's flag, consumers acquire the flags of the halo rows they read (PeerIO).
+            // Flag slots: down-sweep level j = step j; up-sweep level j = step 15 - j.
+            auto io_begin = [&]() {
+                memset(&p.f.io, 0, sizeof(p.f.io));
+                p.f.io.epoch = sp.epoch;
+                p.f.io.error_flag = sp.dev_error;
+                p.f.io.done_counter = flags + 48;
+            };
+            int nwait = 0;
+            auto io_wait = [&](int st) {  // the neighbours' rows of step st must have landed (at most two steps per kernel)
+                if (!first) p.f.io.wait_up[nwait] = flags + st * 2 + 0;
+                if (!last) p.f.io.wait_dn[nwait] = flags + st * 2 + 1;
+                nwait++;
+            };
+            auto io_produce = [&](int st, const unsigned long long *up_a, const unsigned long long *up_b, const unsigned long long *dn_a,
+                                  const unsigned long long *dn_b, int j, size_t rb_a, size_t rb_b, int own_lo, int own_hi, int up_lo,
+                                  int dn_lo) {
+                if (!first) {
+                    p.f.io.up_a = sp.up_base + up_a[j] + (size_t)(own_lo - up_lo) * rb_a;
+                    p.f.io.up_b = up_b ? sp.up_base + up_b[j] + (size_t)(own_lo - up_lo) * rb_b : nullptr;
+                    p.f.io.up_flag = (unsigned *)(sp.up_base + sp.up.flags) + st * 2 + 1;
+                }
+                if (!last) {
+                    p.f.io.dn_a = sp.dn_base + dn_a[j] + (size_t)(own_hi - dn_lo) * rb_a;
+                    p.f.io.dn_b = dn_b ? sp.dn_base + dn_b[j] + (size_t)(own_hi - dn_lo) * rb_b : nullptr;
+                    p.f.io.dn_flag = (unsigned *)(sp.dn_base + sp.dn.flags) + st * 2 + 0;
+                }
+            };
             for (int j = 1; j < p.J; j++) {
+                io_begin();
+                nwait = 0;
+                io_wait(j - 1);  // level j-1 halo rows (step 0 = the input rows for level 1)
+                io_produce(j, sp.up.gp, sp.up.ing, sp.dn.gp, sp.dn.ing, j, (size_t)lb[j].gpitch * p.K * sizeof(float),
+                           (size_t)lb[j].gpitch * sizeof(float), lb[j].cy.lo, lb[j].cy.hi, sp.up.sy_lo[j], sp.dn.sy_lo[j]);
                 launch_down(p, j, s);
-                begin_step();
-                rows_f32(lb[j].gp, sp.up.gp, sp.dn.gp, j, (size_t)lb[j].gpitch * p.K, lb[j].sy.lo, lb[j].cy.lo, lb[j].cy.hi,
-                         sp.up.sy_lo[j], sp.dn.sy_lo[j], 2);
-                rows_f32(lb[j].ing, sp.up.ing, sp.dn.ing, j, (size_t)lb[j].gpitch, lb[j].sy.lo, lb[j].cy.lo, lb[j].cy.hi,
-                         sp.up.sy_lo[j], sp.dn.sy_lo[j], 2);
-                end_step();
             }
             for (int j = p.J - 1; j >= 1; j--) {
+                io_begin();
+                nwait = 0;
+                if (j < p.J - 1) {
+                    io_wait(j + 1);         // gPyramid[j+1] halo rows (only level J-1's have not been waited for yet)
+                    io_wait(15 - (j + 1));  // outGPyramid[j+1] halo rows
+                }
+                io_produce(15 - j, sp.up.outg, nullptr, sp.dn.outg, nullptr, j, (size_t)lb[j].opitch * sizeof(float), 0, lb[j].coy.lo,
+                           lb[j].coy.hi, sp.up.oy_lo[j], sp.dn.oy_lo[j]);
                 launch_up(p, j, s);
-                begin_step();
-                rows_f32(lb[j].outg, sp.up.outg, sp.dn.outg, j, (size_t)lb[j].opitch, lb[j].oy.lo, lb[j].coy.lo, lb[j].coy.hi,
-                         sp.up.oy_lo[j], sp.dn.oy_lo[j], 1);
-                end_step();
             }
+            io_begin();
+            nwait = 0;
+            io_wait(14);  // outGPyramid[1] halo rows
             launch_final(p, s);
+            memset(&p.f.io, 0, sizeof(p.f.io));
         }
     } else {
     hb::Scratch scratch;
