@@ -8,6 +8,7 @@
 // the kernels are compiled into this library.
 #include "hb_common.h"
 
+#include <dlfcn.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -533,6 +534,44 @@ halide_malloc_t halide_set_custom_malloc(halide_malloc_t user_malloc) {
 }
 halide_free_t halide_set_custom_free(halide_free_t user_free) {
     return g_free.exchange(user_free);
+}
+// Default host allocator of the reference runtime: 128-byte aligned (src/runtime/posix_allocator.cpp); tools/RunGenMain.cpp
+// wraps it for its allocation statistics.
+void *halide_default_malloc(void *user_context, size_t x) {
+    void *p = nullptr;
+    if (posix_memalign(&p, 128, x ? x : 1) != 0) return nullptr;
+    return p;
+}
+void halide_default_free(void *user_context, void *ptr) {
+    free(ptr);
+}
+void *halide_malloc(void *user_context, size_t x) {
+    halide_malloc_t m = g_malloc.load();
+    return m ? m(user_context, x) : halide_default_malloc(user_context, x);
+}
+void halide_free(void *user_context, void *ptr) {
+    halide_free_t f = g_free.load();
+    if (f) f(user_context, ptr);
+    else halide_default_free(user_context, ptr);
+}
+// halide_print hook (HalideRuntime.h:170-181)
+static std::atomic<halide_print_t> g_print{nullptr};
+halide_print_t halide_set_custom_print(halide_print_t print) {
+    return g_print.exchange(print);
+}
+void halide_print(void *user_context, const char *msg) {
+    halide_print_t p = g_print.load();
+    if (p) p(user_context, msg);
+    else fputs(msg, stderr);
+}
+// Device allocations are always pooled here (src/runtime/cuda.cpp:760-870 keeps them when enabled); switching reuse off
+// just returns the cached blocks to the driver.
+int halide_reuse_device_allocations(void *user_context, bool enable) {
+    if (!enable) pool().release_unused();
+    return 0;
+}
+void *halide_get_symbol(const char *name) {
+    return dlsym(RTLD_DEFAULT, name);
 }
 
 int halide_device_malloc(void *uc, halide_buffer_t *buf, const halide_device_interface_t *iface) {

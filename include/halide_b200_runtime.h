@@ -187,6 +187,7 @@ struct halide_filter_metadata_t {
 typedef void (*halide_error_handler_t)(void *, const char *);
 typedef void *(*halide_malloc_t)(void *, size_t);
 typedef void (*halide_free_t)(void *, void *);
+typedef void (*halide_print_t)(void *, const char *);
 
 #endif /* HALIDE_HALIDERUNTIME_H */
 
@@ -200,6 +201,19 @@ halide_error_handler_t halide_set_error_handler(halide_error_handler_t handler);
 /* Host allocator hooks (HalideRuntime.h; installed by tools/halide_malloc_trace.h in apps/camera_pipe/process.cpp). */
 halide_malloc_t halide_set_custom_malloc(halide_malloc_t user_malloc);
 halide_free_t halide_set_custom_free(halide_free_t user_free);
+/* The rest of the host-side hooks tools/RunGenMain.cpp links (HalideRuntime.h:170-181,434-465,2343). */
+void *halide_default_malloc(void *user_context, size_t x);
+void halide_default_free(void *user_context, void *ptr);
+void *halide_malloc(void *user_context, size_t x);
+void halide_free(void *user_context, void *ptr);
+halide_print_t halide_set_custom_print(halide_print_t print);
+void halide_print(void *user_context, const char *msg);
+void *halide_get_symbol(const char *name);
+#ifdef __cplusplus
+int halide_reuse_device_allocations(void *user_context, bool enable);
+#else
+int halide_reuse_device_allocations(void *user_context, _Bool enable);
+#endif
 
 /* Device bookkeeping (src/runtime/device_interface.cpp:30-56,154-205). */
 int halide_device_malloc(void *user_context, struct halide_buffer_t *buf,

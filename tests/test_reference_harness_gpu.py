@@ -110,3 +110,14 @@ def test_camera_pipe_process_cpp(tmp_path, oracle):
 def test_conv_layer_process_cpp():
     out = _run([_bin("conv_process")])
     assert "Manually-tuned time" in out and "Auto-scheduled time" in out
+
+
+@pytest.mark.parametrize("name", ["local_laplacian", "bilateral_grid", "stencil_chain", "conv_layer"])
+def test_rungen_benchmark_mode(name):
+    """the reference's generic driver (tools/RunGenMain.cpp, unmodified) linked with our registration
+    TU sizes its buffers through our bounds-query mode, fills them from the metadata estimates and times the filter —
+    the command `ctest -L benchmark_apps` runs (apps/local_laplacian/CMakeLists.txt:62-70)."""
+    r = subprocess.run([_bin(name + "_rungen"), "--benchmarks=all", "--estimate_all", "--parsable_output"], capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "BEST_TIME_MSEC_PER_ITER" in r.stdout, r.stdout + r.stderr
