@@ -13,9 +13,22 @@
 // Block = 10x8 output pixels x 128 output channels, 256 threads, each thread 5 pixels x 8 channels in registers;
 // per (ci-chunk of 32, ky, kx) one 16 KB filter slab is staged in shared memory; the input patch (12x10 pixels
 // x 32 channels) is staged once per ci-chunk.  Operand loads are warp-broadcast or 16-byte conflict-free.
+#include <stdlib.h>
+#include <string.h>
+
 #include "hb_common.h"
 
+// tcgen05 / TMEM / TMA implementation (conv_layer_tc.cu)
+int conv_layer_tc_run(const float *din, const float *df, const float *db, float *dout, cudaStream_t s);
+
 namespace {
+
+// Which contraction runs: the tcgen05 implicit GEMM (3xTF32 split) or the FP32 SIMT kernel.  HALIDE_B200_CONV=simt|tc
+// picks at start-up; halide_b200_conv_use_tensor_cores() switches at run time (tests cover both).
+bool g_use_tc = [] {
+    const char *e = getenv("HALIDE_B200_CONV");
+    return !(e && strcmp(e, "simt") == 0);  // default: tensor cores
+}();
 
 constexpr int N = 5, CI = 128, CO = 128, W = 100, H = 80;  // generator :35-50 (process.cpp:14)
 constexpr int TX = 10, TY = 8;                             // output tile
@@ -156,9 +169,13 @@ int run_conv_layer(halide_buffer_t *input, halide_buffer_t *filter, halide_buffe
     cudaStream_t s = hb::stream();
     {
         hb::CallTimer timer(s);
-        dim3 grid(W / TX, H / TY, N);
-        HB_LAUNCH("conv_layer_f32", conv_layer_kernel, grid, 256, 0, s, (const float *)din, (const float *)df, (const float *)db,
-                  (float *)dout);
+        if (g_use_tc) {
+            if ((r = conv_layer_tc_run((const float *)din, (const float *)df, (const float *)db, (float *)dout, s))) return r;
+        } else {
+            dim3 grid(W / TX, H / TY, N);
+            HB_LAUNCH("conv_layer_f32", conv_layer_kernel, grid, 256, 0, s, (const float *)din, (const float *)df, (const float *)db,
+                      (float *)dout);
+        }
     }
     if ((r = hb::check_cuda(cudaGetLastError(), "conv_layer launch", halide_error_code_device_run_failed))) return r;
     hb::mark_output_written(relu);
@@ -184,4 +201,8 @@ extern "C" int conv_layer_auto_schedule_argv(void **a) {
 }
 extern "C" const halide_filter_metadata_t *conv_layer_auto_schedule_metadata(void) {
     return &kMetaAuto;
+}
+
+extern "C" void halide_b200_conv_use_tensor_cores(int enable) {
+    g_use_tc = enable != 0;
 }

@@ -279,6 +279,8 @@ int halide_b200_ll_band_geometry(int32_t frame_w, int32_t frame_h, int32_t band_
 /* Test hook: bitmask routing levels==8 calls through the generic kernels (1 down, 2 up, 4 final,
  * 8 no fused coarse launch) so both code paths stay covered by the parity tests. */
 void halide_b200_ll_force_generic(int mask);
+/* conv_layer: 1 = tcgen05/TMEM/TMA implicit GEMM (3xTF32 split), 0 = FP32 SIMT kernel (also HALIDE_B200_CONV=tc|simt). */
+void halide_b200_conv_use_tensor_cores(int enable);
 /* Device self-test of the fast kernels' arithmetic shortcuts; returns mismatches vs div.rn / cvt, or -1. */
 long long halide_b200_selftest_arith(unsigned long long n, unsigned long long seed);
 
