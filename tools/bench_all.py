@@ -128,7 +128,7 @@ def main():
     t = time_gpu(mk, lambda o: filters.conv_layer(bi, bf, bb, o), 20)
     ci, cf, cb = ti[:1].cpu().numpy(), tf.cpu().numpy(), tb.cpu().numpy()
     report("conv_layer", "N5 CI128 CO128 100x80 3x3 f32", 5 * 80 * 100, 42.5e6, t, cpu_time(lambda: pyoracle.conv_layer(ci, cf, cb), 1) * 5,
-           "1 of 5 images x5", bound="fp32 (tensor cores: next)", flops=11.8e9)
+           "1 of 5 images x5", bound="tensor (tcgen05 kind::tf32, 3-term split)", flops=11.8e9)
     # ---- local_laplacian (headline; bench.py measures it with the full contract)
     for (W, H) in [(3840, 2160), (16384, 2048)] + ([] if quick else [(16384, 16384)]):
         def mk():
