@@ -47,16 +47,29 @@ __device__ __forceinline__ uint4 load_chunk(const uint16_t *p, int64_t off, int6
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// blur_x for the 8 pixels of this lane on one input row.
-__device__ __forceinline__ void blur_x_row(const BlurArgs &a, int64_t row_off, int x0, int lane, uint32_t bx[8]) {
+// Raw 16-byte chunks of one input row for this lane (issued one row ahead of their use so the loads of row y+3
+// are in flight while row y+2 is being reduced).
+struct RawRow {
+    uint4 v, t;
+    int mis;
+};
+__device__ __forceinline__ RawRow load_raw_row(const BlurArgs &a, int64_t row_off, int x0, int lane) {
+    RawRow r;
     // Element offset (relative to a.in) of the first pixel of this warp's strip on this row.
     int64_t e = row_off + x0;
     // Misalignment of that element against 16 bytes, uniform across the warp.
-    int mis = (int)((reinterpret_cast<uintptr_t>(a.in + e) & 15) >> 1);
-    int64_t base = e - mis;  // 16-byte aligned
-    uint4 v = load_chunk(a.in, base + 8 * lane, a.in_lo, a.in_hi);
-    uint4 t = make_uint4(0, 0, 0, 0);
-    if (lane < 2) t = load_chunk(a.in, base + 8 * (32 + lane), a.in_lo, a.in_hi);
+    r.mis = (int)((reinterpret_cast<uintptr_t>(a.in + e) & 15) >> 1);
+    int64_t base = e - r.mis;  // 16-byte aligned
+    r.v = load_chunk(a.in, base + 8 * lane, a.in_lo, a.in_hi);
+    r.t = make_uint4(0, 0, 0, 0);
+    if (lane < 2) r.t = load_chunk(a.in, base + 8 * (32 + lane), a.in_lo, a.in_hi);
+    return r;
+}
+
+// blur_x for the 8 pixels of this lane on one input row.
+__device__ __forceinline__ void blur_x_row(const RawRow &raw, int lane, uint32_t bx[8]) {
+    const uint4 v = raw.v, t = raw.t;
+    const int mis = raw.mis;
 
     // words of the 3-chunk window: own chunk, next lane's chunk, first word of the chunk after that
     uint32_t w[9];
@@ -105,11 +118,14 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) blur3x3_u16_kernel(BlurAr
     int y1 = min(y0 + a.rows_per_warp, a.h);
 
     uint32_t r0[8], r1[8], r2[8];
-    blur_x_row(a, (int64_t)y0 * a.in_stride_y, x0, lane, r0);
-    blur_x_row(a, (int64_t)(y0 + 1) * a.in_stride_y, x0, lane, r1);
+    blur_x_row(load_raw_row(a, (int64_t)y0 * a.in_stride_y, x0, lane), lane, r0);
+    blur_x_row(load_raw_row(a, (int64_t)(y0 + 1) * a.in_stride_y, x0, lane), lane, r1);
+    RawRow next = load_raw_row(a, (int64_t)(y0 + 2) * a.in_stride_y, x0, lane);
     int xl = x0 + lane * kPxPerLane;
     for (int y = y0; y < y1; y++) {
-        blur_x_row(a, (int64_t)(y + 2) * a.in_stride_y, x0, lane, r2);
+        const RawRow cur = next;
+        if (y + 1 < y1) next = load_raw_row(a, (int64_t)(y + 3) * a.in_stride_y, x0, lane);
+        blur_x_row(cur, lane, r2);
         uint32_t o[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) o[i] = ((r0[i] + r1[i] + r2[i]) & 0xffffu) / 3u;

@@ -19,6 +19,7 @@
 //            tcgen05.commit -> the stage's "empty" barrier / the accumulator's "full" barrier
 //   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per instruction), + bias, relu, 128-byte row stores
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "hb_common.h"
 
@@ -28,18 +29,21 @@ constexpr int N = 5, CI = 128, CO = 128, W = 100, H = 80;
 constexpr int WP = W + 2, HP = H + 2;
 constexpr int ROWS_PER_IMAGE = HP * WP;          // 8364 input rows per image
 constexpr int A_ROWS = N * ROWS_PER_IMAGE;       // 41820
-constexpr int TILE_M = 128, TILE_N = 128, TILE_K = 32;  // 32 tf32 = 128 bytes = one swizzle row
+constexpr int TILE_M = 128, TILE_K = 32;  // 32 tf32 = 128 bytes = one swizzle row; the N tile is a template parameter (64 or 128)
 constexpr int TILES_PER_IMAGE = (H * WP + TILE_M - 1) / TILE_M;  // 64 (outputs enumerated over the padded width)
 constexpr int K_STEPS = 9 * (CI / TILE_K);       // 36
 constexpr int STAGES = 3;
-constexpr int TILE_BYTES = TILE_M * TILE_K * 4;  // 16 KB
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-constexpr int ACCS = 4;                        // partial accumulators (see the MMA issuer)
-constexpr uint32_t TMEM_COLS = ACCS * TILE_N;  // 512: the whole tensor memory of the SM
+constexpr int A_TILE_BYTES = TILE_M * TILE_K * 4;  // 16 KB
+constexpr int ACCS = 4;                          // partial accumulators (see the MMA issuer)
+template<int NT> struct Cfg {
+    static constexpr int B_TILE_BYTES = NT * TILE_K * 4;
+    static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // A_hi, A_lo, B_hi, B_lo
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr uint32_t TMEM_COLS = ACCS * NT;  // 512 (the whole tensor memory of the SM) or 256
+    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+};
 // instruction descriptor (cute/arch/mma_sm100_desc.hpp: InstrDescriptor): c=F32 [4,6)=1, a=TF32 [7,10)=2, b=TF32 [10,13)=2,
 // a/b K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((TILE_N >> 3) << 17) | ((TILE_M >> 4) << 24);
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -68,7 +72,7 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
 __device__ __forceinline__ uint64_t umma_desc(const void *tile) {
     return (uint64_t)((smem_u32(tile) & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate, uint32_t IDESC) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
@@ -105,11 +109,15 @@ __global__ void conv_prep_filter_kernel(const float *__restrict__ f, float *__re
 }
 
 // ---- the GEMM ---------------------------------------------------------------------------------------------------------
+template<int NT>
 __global__ void __launch_bounds__(192, 1) conv_layer_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                                                                const __grid_constant__ CUtensorMap map_a_lo,
                                                                const __grid_constant__ CUtensorMap map_b_hi,
                                                                const __grid_constant__ CUtensorMap map_b_lo,
                                                                const float *__restrict__ bias, float *__restrict__ out) {
+    constexpr int TILE_N = NT, TILE_BYTES = A_TILE_BYTES, STAGE_BYTES = Cfg<NT>::STAGE_BYTES;
+    constexpr uint32_t TMEM_COLS = Cfg<NT>::TMEM_COLS, IDESC = Cfg<NT>::IDESC;
+    const int n0 = blockIdx.z * NT;  // first output channel of this CTA
     extern __shared__ uint8_t smem_raw[];
     uint8_t *tiles = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B needs 1024-byte alignment
     uint64_t *full_bar = (uint64_t *)(tiles + STAGES * STAGE_BYTES);
@@ -150,8 +158,8 @@ __global__ void __launch_bounds__(192, 1) conv_layer_tc_kernel(const __grid_cons
                 mbar_expect_tx(&full_bar[s], STAGE_BYTES);
                 tma_load_2d(st + 0 * TILE_BYTES, &map_a_hi, &full_bar[s], kc * TILE_K, a_row0 + ky * WP + kx);
                 tma_load_2d(st + 1 * TILE_BYTES, &map_a_lo, &full_bar[s], kc * TILE_K, a_row0 + ky * WP + kx);
-                tma_load_2d(st + 2 * TILE_BYTES, &map_b_hi, &full_bar[s], kc * TILE_K, tap * CO);
-                tma_load_2d(st + 3 * TILE_BYTES, &map_b_lo, &full_bar[s], kc * TILE_K, tap * CO);
+                tma_load_2d(st + 2 * TILE_BYTES, &map_b_hi, &full_bar[s], kc * TILE_K, tap * CO + n0);
+                tma_load_2d(st + 2 * TILE_BYTES + Cfg<NT>::B_TILE_BYTES, &map_b_lo, &full_bar[s], kc * TILE_K, tap * CO + n0);
             }
         }
     } else if (warp == 1) {
@@ -163,7 +171,7 @@ __global__ void __launch_bounds__(192, 1) conv_layer_tc_kernel(const __grid_cons
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint8_t *st = tiles + s * STAGE_BYTES;
                 const uint64_t a_hi = umma_desc(st + 0 * TILE_BYTES), a_lo = umma_desc(st + 1 * TILE_BYTES);
-                const uint64_t b_hi = umma_desc(st + 2 * TILE_BYTES), b_lo = umma_desc(st + 3 * TILE_BYTES);
+                const uint64_t b_hi = umma_desc(st + 2 * TILE_BYTES), b_lo = umma_desc(st + 2 * TILE_BYTES + Cfg<NT>::B_TILE_BYTES);
                 // The tensor core adds into the fp32 accumulator with truncation; 432 chained adds biased the result by
                 // ~-2.5e-5 relative (measured).  Four partial accumulators (K steps round-robin) cut the chain to 108 adds
                 // each; the epilogue sums them in round-to-nearest.
@@ -171,9 +179,9 @@ __global__ void __launch_bounds__(192, 1) conv_layer_tc_kernel(const __grid_cons
 #pragma unroll
                 for (int k = 0; k < TILE_K / 8; k++) {  // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 2 (16-byte units)
                     const uint64_t adv = (uint64_t)(2 * k);
-                    umma_tf32(acc, a_hi + adv, b_hi + adv, (it >= ACCS) || (k != 0));
-                    umma_tf32(acc, a_hi + adv, b_lo + adv, 1);
-                    umma_tf32(acc, a_lo + adv, b_hi + adv, 1);
+                    umma_tf32(acc, a_hi + adv, b_hi + adv, (it >= ACCS) || (k != 0), IDESC);
+                    umma_tf32(acc, a_hi + adv, b_lo + adv, 1, IDESC);
+                    umma_tf32(acc, a_lo + adv, b_hi + adv, 1, IDESC);
                 }
                 umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have consumed it
             }
@@ -210,13 +218,13 @@ __global__ void __launch_bounds__(192, 1) conv_layer_tc_kernel(const __grid_cons
             if (valid) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    float4 b = __ldg(reinterpret_cast<const float4 *>(bias + c0 + j));
+                    float4 b = __ldg(reinterpret_cast<const float4 *>(bias + n0 + c0 + j));
                     float4 v;
                     v.x = fmaxf(r[j] + b.x, 0.f);
                     v.y = fmaxf(r[j + 1] + b.y, 0.f);
                     v.z = fmaxf(r[j + 2] + b.z, 0.f);
                     v.w = fmaxf(r[j + 3] + b.w, 0.f);
-                    *reinterpret_cast<float4 *>(orow + c0 + j) = v;
+                    *reinterpret_cast<float4 *>(orow + n0 + c0 + j) = v;
                 }
             }
         }
@@ -232,10 +240,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_map(EncodeTiledFn enc, CUtensorMap *m, void *base, uint64_t rows) {
+int make_map(EncodeTiledFn enc, CUtensorMap *m, void *base, uint64_t rows, int box_rows) {
     cuuint64_t dims[2] = {(cuuint64_t)CI, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)CI * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)TILE_K, (cuuint32_t)TILE_M};
+    cuuint32_t box[2] = {(cuuint32_t)TILE_K, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -261,19 +269,32 @@ int conv_layer_tc_run(const float *din, const float *df, const float *db, float 
     float *a_hi = scratch.get<float>(a_elems), *a_lo = scratch.get<float>(a_elems);
     float *b_hi = scratch.get<float>(b_elems), *b_lo = scratch.get<float>(b_elems);
     if (!a_hi || !a_lo || !b_hi || !b_lo) return hb::fail(halide_error_code_device_malloc_failed, "conv_layer: scratch allocation failed");
+    // Tile width: 128x128 (320 CTAs, 2.16 waves) measured 84.7 us per call; 128x64 (640 CTAs, 4.3 waves, selectable with
+    // HALIDE_B200_CONV_NT=64) removes the tail wave but measured 114.5 us — the narrower MMA re-reads A twice from shared memory.
+    static const int nt = [] {
+        const char *e = getenv("HALIDE_B200_CONV_NT");
+        return (e && atoi(e) == 64) ? 64 : 128;
+    }();
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-    if (make_map(enc, &ma_hi, a_hi, A_ROWS) || make_map(enc, &ma_lo, a_lo, A_ROWS) || make_map(enc, &mb_hi, b_hi, 9 * CO) ||
-        make_map(enc, &mb_lo, b_lo, 9 * CO)) {
+    if (make_map(enc, &ma_hi, a_hi, A_ROWS, TILE_M) || make_map(enc, &ma_lo, a_lo, A_ROWS, TILE_M) ||
+        make_map(enc, &mb_hi, b_hi, 9 * CO, nt) || make_map(enc, &mb_lo, b_lo, 9 * CO, nt)) {
         return hb::fail(halide_error_code_generic_error, "conv_layer: cuTensorMapEncodeTiled failed");
     }
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(conv_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(conv_layer_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM_BYTES);
+        cudaFuncSetAttribute(conv_layer_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES);
         attr = true;
     }
     HB_LAUNCH("conv_split_input", conv_split_input_kernel, (unsigned)((a_elems / 4 + 255) / 256), 256, 0, s, (const float4 *)din, (float4 *)a_hi,
               (float4 *)a_lo, a_elems / 4);
     HB_LAUNCH("conv_prep_filter", conv_prep_filter_kernel, (unsigned)((b_elems + 255) / 256), 256, 0, s, df, b_hi, b_lo);
-    HB_LAUNCH("conv_layer_tc", conv_layer_tc_kernel, dim3(TILES_PER_IMAGE, N), 192, SMEM_BYTES, s, ma_hi, ma_lo, mb_hi, mb_lo, db, dout);
+    if (nt == 64) {
+        HB_LAUNCH("conv_layer_tc", conv_layer_tc_kernel<64>, dim3(TILES_PER_IMAGE, N, 2), 192, Cfg<64>::SMEM_BYTES, s, ma_hi, ma_lo, mb_hi,
+                  mb_lo, db, dout);
+    } else {
+        HB_LAUNCH("conv_layer_tc", conv_layer_tc_kernel<128>, dim3(TILES_PER_IMAGE, N, 1), 192, Cfg<128>::SMEM_BYTES, s, ma_hi, ma_lo, mb_hi,
+                  mb_lo, db, dout);
+    }
     return 0;
 }

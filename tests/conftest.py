@@ -34,6 +34,8 @@ def oracle():
     """The CPU oracle (test infrastructure).  Built on demand with oracle/Makefile."""
     from oracle import pyoracle
     pyoracle.lib()
+    # the oracle's many small OpenMP regions crawl on very wide hosts (measured: 128 threads is ~10x slower than 16)
+    pyoracle.set_threads(min(16, pyoracle.use_all_cores()))
     return pyoracle
 
 
