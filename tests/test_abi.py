@@ -107,3 +107,64 @@ def test_bounds_query_mode(hb):
     q3 = HalideBuffer.bounds_query(np.uint16, 3)
     assert filters.local_laplacian(q3, 8, 1 / 7, 1.0, out3) == 0
     assert q3.shape() == [(0, 30, 1), (0, 20, 30), (0, 3, 600)]
+
+
+def _expect(code, fn, *args):
+    from halide_b200 import HalideError
+    with pytest.raises(HalideError) as e:
+        fn(*args)
+    assert e.value.code == code, (e.value.code, e.value.message)
+
+
+def test_per_filter_validation_without_gpu(hb):
+    """Every filter validates before touching CUDA: wrong types / shapes / regions return the generated-code error codes."""
+    import numpy as np
+    from halide_b200 import HalideBuffer as B, filters as F
+    f32, u16, u8 = np.float32, np.uint16, np.uint8
+    # bilateral_grid: float 2-D in/out, input must cover the output
+    _expect(-3, F.bilateral_grid, B.from_numpy(np.zeros((8, 8), u16)), 0.1, B.from_numpy(np.zeros((8, 8), f32)))
+    _expect(-4, F.bilateral_grid, B.from_numpy(np.zeros((8, 8), f32)), 0.1, B.from_numpy(np.zeros((9, 8), f32)))
+    _expect(-9, F.bilateral_grid, B.from_numpy(np.zeros((8, 8), f32)), 0.0, B.from_numpy(np.zeros((8, 8), f32)))
+    # nl_means: 3-D float, output channels fixed to [0,3)
+    _expect(-43, F.nl_means, B.from_numpy(np.zeros((8, 8), f32)), 3, 7, 0.12, B.from_numpy(np.zeros((3, 8, 8), f32)))
+    _expect(-8, F.nl_means, B.from_numpy(np.zeros((3, 8, 8), f32)), 3, 7, 0.12, B.from_numpy(np.zeros((4, 8, 8), f32)))
+    _expect(-9, F.nl_means, B.from_numpy(np.zeros((3, 8, 8), f32)), 0, 7, 0.12, B.from_numpy(np.zeros((3, 8, 8), f32)))
+    # stencil_chain: u16 2-D; stride[0] must be 1
+    _expect(-3, F.stencil_chain, B.from_numpy(np.zeros((8, 8), f32)), B.from_numpy(np.zeros((8, 8), u16)))
+    bad = B.from_numpy(np.zeros((8, 8), u16))
+    bad.dims[0].stride = 2
+    _expect(-8, F.stencil_chain, bad, B.from_numpy(np.zeros((8, 8), u16)))
+    # conv_layer: fixed shapes and strides (generator constraints)
+    ok_in, ok_f, ok_b = np.zeros((5, 82, 102, 128), f32), np.zeros((128, 3, 3, 128), f32), np.zeros((128,), f32)
+    _expect(-8, F.conv_layer, B.from_numpy(ok_in), B.from_numpy(ok_f), B.from_numpy(ok_b), B.from_numpy(np.zeros((5, 80, 100, 64), f32)))
+    _expect(-43, F.conv_layer, B.from_numpy(ok_in), B.from_numpy(ok_f), B.from_numpy(np.zeros((1, 128), f32)),
+            B.from_numpy(np.zeros((5, 80, 100, 128), f32)))
+    # camera_pipe: raw must cover the stencil footprint after the (16,12) shift; output is u8 with at most channels 0..2
+    m = np.zeros((3, 4), f32)
+    _expect(-4, F.camera_pipe, B.from_numpy(np.zeros((64, 64), u16)), B.from_numpy(m), B.from_numpy(m), 3700.0, 2.0, 50.0, 1.0, 25, 1023,
+            B.from_numpy(np.zeros((3, 64, 64), u8)))
+    _expect(-3, F.camera_pipe, B.from_numpy(np.zeros((120, 160), u16)), B.from_numpy(m), B.from_numpy(m), 3700.0, 2.0, 50.0, 1.0, 25, 1023,
+            B.from_numpy(np.zeros((3, 64, 96), u16)))
+    # local_laplacian: levels range
+    _expect(-9, F.local_laplacian, B.from_numpy(np.zeros((3, 8, 8), u16)), 1, 1.0, 1.0, B.from_numpy(np.zeros((3, 8, 8), u16)))
+
+
+def test_per_filter_bounds_queries(hb):
+    import numpy as np
+    from halide_b200 import HalideBuffer as B, filters as F
+    # camera_pipe asks for the shifted footprint of the output region (harness: 2560x1920 out of a 2592x1968 raw)
+    q = B.bounds_query(np.uint16, 2)
+    m = np.zeros((3, 4), np.float32)
+    out = B.from_numpy(np.zeros((3, 1920, 2560), np.uint8))
+    assert F.camera_pipe(q, B.from_numpy(m), B.from_numpy(m), 3700.0, 2.0, 50.0, 1.0, 25, 1023, out) == 0
+    (x0, w, _), (y0, h, _) = q.shape()
+    assert x0 >= 0 and y0 >= 0 and x0 + w <= 2592 and y0 + h <= 1968  # fits the harness's raw frame
+    # conv_layer proposes its fixed shapes
+    qi, qf, qb = B.bounds_query(np.float32, 4), B.bounds_query(np.float32, 4), B.bounds_query(np.float32, 1)
+    qo = B.bounds_query(np.float32, 4)
+    assert F.conv_layer(qi, qf, qb, qo) == 0
+    assert [e for (_, e, _) in qi.shape()] == [128, 102, 82, 5] and [e for (_, e, _) in qo.shape()] == [128, 100, 80, 5]
+    # nl_means: every access is clamped -> input region == output region, 3 channels
+    q3 = B.bounds_query(np.float32, 3)
+    assert F.nl_means(q3, 3, 7, 0.12, B.from_numpy(np.zeros((3, 20, 30), np.float32))) == 0
+    assert [e for (_, e, _) in q3.shape()] == [30, 20, 3]
