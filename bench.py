@@ -316,7 +316,43 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(e2e_steps):
         e2e_step()
     barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_serial_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_s, e2e_mode = e2e_serial_s, "one caller thread: H2D, kernels, D2H back to back"
+    if world == 1:
+        # A caller with several frames in hand (video) keeps DEPTH frames in flight, one thread + CUDA stream each
+        # (halide_b200.FramePipeline): every step still copies its own input up and its own result down inside the
+        # timed region, but frame i's D2H overlaps frame i+1's kernels and frame i+2's H2D on the full-duplex link.
+        from halide_b200 import FramePipeline
+        DEPTH = 3
+        slots = []
+        for k in range(DEPTH):
+            hi = torch.empty((3, H, W), dtype=torch.uint16).pin_memory()
+            hi.view(torch.int16).copy_(ins[k % NSETS].view(torch.int16))
+            ho = torch.empty((3, H, W), dtype=torch.uint16).pin_memory()
+            bi, bo = HalideBuffer.from_torch(hi), HalideBuffer.from_torch(ho)
+            bo.set_host_dirty(False)
+            slots.append((bi, bo, hi, ho))
+
+        def job(k):
+            bi, bo = slots[k][0], slots[k][1]
+            bi.set_host_dirty(True)
+            filters.local_laplacian(bi, LEVELS, ALPHA, BETA, bo)
+            bo.copy_to_host()
+
+        pipe_steps = 3 * e2e_steps
+        with FramePipeline(DEPTH, device=local_rank) as fp:
+            for t in [fp.submit(job, k % DEPTH, slot=k % DEPTH) for k in range(2 * DEPTH)]:
+                fp.result(t)
+            t0 = time.perf_counter()
+            for t in [fp.submit(job, k % DEPTH, slot=k % DEPTH) for k in range(pipe_steps)]:
+                fp.result(t)
+            e2e_pipe_s = (time.perf_counter() - t0) / pipe_steps
+        # the pipelined frames must be the same bits as the serial call's
+        if not torch.equal(slots[0][3].view(torch.int16), h_out.view(torch.int16)):
+            raise SystemExit("bench: pipelined e2e output differs from the serial call")
+        if e2e_pipe_s < e2e_s:
+            e2e_s, e2e_steps = e2e_pipe_s, pipe_steps
+            e2e_mode = "FramePipeline depth %d: %d caller threads, one CUDA stream each" % (DEPTH, DEPTH)
     if dist is not None:
         tt = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -366,7 +402,8 @@ def run_ours(args, rank, world, local_rank):
                        "l2": f"rotating {NSETS} device-resident frame pairs ({NSETS * 2 * nbytes / 1e6:.0f} MB) > 126 MB L2",
                        "input": "uniform random uint16 (torch.randint), worst case for the LUT gathers"},
             "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-                    "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "host_memory": "pinned"},
+                    "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "host_memory": "pinned", "mode": e2e_mode,
+                    "serial_ms_per_step": e2e_serial_s * 1e3},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
             "kernels": kernels, "extra": {"smooth_frame_Mpixels_per_s": smooth_value,
                                            "note": "same call on a low-frequency synthetic frame (coherent LUT / plane gathers); context only"}}

@@ -10,3 +10,4 @@ from .buffer import HalideBuffer, halide_buffer_t, halide_dimension_t  # noqa: F
 from .lib import lib as capi, load_library, HalideError, capture_errors  # noqa: F401
 from . import lib  # noqa: F401  (module: loader + profile helpers)
 from . import filters  # noqa: F401
+from .pipeline import FramePipeline  # noqa: F401

@@ -26,12 +26,15 @@ std::atomic<uint64_t> g_launches{0};
 thread_local cudaStream_t t_stream = nullptr;
 
 // ---- device allocation pool ------------------------------------------------------------------
-// Exact-size free lists.  Blocks returned by device_free / scratch_free become reusable by later
-// work on the same stream without a sync (stream order makes that safe); they go back to the
-// driver only through halide_cuda_release_unused_device_allocations / halide_device_release.
+// Exact-size free lists, one per stream.  Blocks returned by device_free / scratch_free become reusable
+// by later work on the *same* stream without a sync (stream order makes that safe); a caller thread that
+// runs on its own stream (halide_b200_set_stream is thread-local) therefore never receives a block whose
+// last use is still in flight on another thread's stream.  Blocks go back to the driver only through
+// halide_cuda_release_unused_device_allocations / halide_device_release.
 struct Pool {
+    using Key = std::pair<cudaStream_t, size_t>;
     std::mutex mu;
-    std::multimap<size_t, void *> free_blocks;
+    std::multimap<Key, void *> free_blocks;
     std::map<void *, size_t> live;
     size_t cached_bytes = 0;
 
@@ -40,7 +43,7 @@ struct Pool {
         bytes = (bytes + 255) & ~size_t(255);
         {
             std::lock_guard<std::mutex> lock(mu);
-            auto it = free_blocks.find(bytes);
+            auto it = free_blocks.find(Key(t_stream, bytes));
             if (it != free_blocks.end()) {
                 void *p = it->second;
                 free_blocks.erase(it);
@@ -68,7 +71,7 @@ struct Pool {
         std::lock_guard<std::mutex> lock(mu);
         auto it = live.find(p);
         if (it == live.end()) return;  // wrapped / foreign pointer: not ours to recycle
-        free_blocks.emplace(it->second, p);
+        free_blocks.emplace(Key(t_stream, it->second), p);
         cached_bytes += it->second;
         live.erase(it);
     }
@@ -626,6 +629,24 @@ void halide_b200_set_stream(void *s) {
 }
 void *halide_b200_get_stream(void) {
     return (void *)t_stream;
+}
+void *halide_b200_stream_create(void) {
+    cudaStream_t s = nullptr;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) {
+        hb::fail(halide_error_code_gpu_device_error, "CUDA: stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return (void *)s;
+}
+int halide_b200_stream_destroy(void *stream) {
+    if (!stream) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaStreamSynchronize(s);
+    if (t_stream == s) t_stream = nullptr;
+    if (cudaStreamDestroy(s) != cudaSuccess) {
+        return hb::fail(halide_error_code_gpu_device_error, "CUDA: stream destroy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    return 0;
 }
 int halide_b200_set_device(int ordinal) {
     cudaError_t e = cudaSetDevice(ordinal);

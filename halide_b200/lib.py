@@ -53,6 +53,8 @@ def load_library():
         l.halide_b200_last_kernel_ms.restype = ctypes.c_float
         l.halide_b200_set_stream.argtypes = [ctypes.c_void_p]
         l.halide_b200_get_stream.restype = ctypes.c_void_p
+        l.halide_b200_stream_create.restype = ctypes.c_void_p
+        l.halide_b200_stream_destroy.argtypes = [ctypes.c_void_p]
         l.halide_cuda_device_interface.restype = ctypes.c_void_p
         l.halide_b200_profile_report.argtypes = [ctypes.c_char_p, ctypes.c_int]
         # The reference's default handler aborts the process (posix_error_handler.cpp); from

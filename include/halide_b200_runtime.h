@@ -239,6 +239,10 @@ int halide_cuda_release_unused_device_allocations(void *user_context);
  * default current stream).  Replaces halide_set_cuda_get_stream (HalideRuntimeCuda.h:66-81). */
 void halide_b200_set_stream(void *cuda_stream);
 void *halide_b200_get_stream(void);
+/* A non-blocking stream for a caller thread that pipelines frames (one stream per thread: copies of
+ * one thread's frame overlap kernels and copies of another's); destroy synchronises first. */
+void *halide_b200_stream_create(void);
+int halide_b200_stream_destroy(void *cuda_stream);
 /* Select the CUDA device for this process (replaces HL_GPU_DEVICE, src/runtime/gpu_device_selection.cpp). */
 int halide_b200_set_device(int ordinal);
 /* Number of kernels this library has launched since process start (bench.py's gpu_launches). */
