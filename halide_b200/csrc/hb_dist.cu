@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(256) peer_exchange_kernel(PeerXchg x) {
             __threadfence_system();
             if (x.peer_flag[0]) st_release_sys(x.peer_flag[0], x.epoch);
             if (x.peer_flag[1]) st_release_sys(x.peer_flag[1], x.epoch);
+            for (int i = 0; i < x.nready; i++) st_release_sys(x.ready_flag[i], x.epoch);
         }
     }
     // 3. wait for the neighbours' rows of this step (block 0 only; bounded spin so a protocol bug cannot hang the GPU)
@@ -163,10 +164,57 @@ __global__ void __launch_bounds__(256) peer_exchange_kernel(PeerXchg x) {
     }
 }
 
+__device__ __forceinline__ void spin_until(const unsigned *flag, unsigned epoch, unsigned *error_flag) {
+    long long t0 = clock64();
+    while ((int)(ld_acquire_sys(flag) - epoch) < 0) {  // epochs only grow
+        if (clock64() - t0 > 4000000000LL) {            // ~2 s: report instead of hanging the GPU
+            *error_flag = 1u;
+            break;
+        }
+        __nanosleep(100);
+    }
+}
+
+__global__ void __launch_bounds__(256) peer_gather_kernel(PeerGather x) {
+    // 0. no peer's copy may be overwritten before that peer has drained its previous call
+    if ((int)threadIdx.x < x.npeer) spin_until(x.ready[threadIdx.x], x.epoch, x.error_flag);
+    __syncthreads();
+    // 1. push my rows into every peer's copy (16-byte elements; rows are 16-byte multiples)
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int i = 0; i < x.nseg; i++) {
+        const PeerSeg &g = x.seg[i];
+        const uint4 *s = reinterpret_cast<const uint4 *>(g.src);
+        uint4 *d = reinterpret_cast<uint4 *>(g.dst);
+        for (unsigned k = tid; k < g.bytes / 16; k += nth) d[k] = s[k];
+    }
+    // 2. the last block to finish announces the rows to every peer
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) {
+        unsigned prev = atomicAdd(x.done_counter, 1u);
+        s_last = prev == gridDim.x - 1;
+        if (s_last) {
+            *x.done_counter = 0u;
+            __threadfence_system();
+        }
+    }
+    __syncthreads();
+    if (s_last) {
+        if ((int)threadIdx.x < x.npeer) st_release_sys(x.peer_flag[threadIdx.x], x.epoch);
+        // 3. ... and waits for theirs; the kernel boundary then orders the gathered rows before the consumers
+        if ((int)threadIdx.x < x.npeer) spin_until(x.my_flag[threadIdx.x], x.epoch, x.error_flag);
+        __threadfence_system();
+    }
+}
+
 }  // namespace
 
 void launch_peer_exchange(const PeerXchg &x, cudaStream_t s) {
     HB_LAUNCH("peer_exchange", peer_exchange_kernel, 8, 256, 0, s, x);
+}
+void launch_peer_gather(const PeerGather &g, cudaStream_t s) {
+    HB_LAUNCH("peer_gather", peer_gather_kernel, 64, 256, 0, s, g);
 }
 
 }  // namespace hbdist

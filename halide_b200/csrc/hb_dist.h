@@ -40,7 +40,28 @@ struct PeerXchg {
     unsigned epoch;
     unsigned *done_counter;      // local scratch counter (self-resetting)
     unsigned *error_flag;        // set to 1 on wait timeout
+    unsigned *ready_flag[8];     // "my previous call has drained" announcements to every other rank (see PeerGather)
+    int nready;
 };
 void launch_peer_exchange(const PeerXchg &x, cudaStream_t s);
+
+// ---- all-to-all gather of one (small) pyramid level --------------------------------------------------------
+// Every rank stores its band of the level into the same rows of every other rank's copy, so that the levels
+// below it can be computed redundantly on every rank with no further exchange.  Before overwriting a peer's copy
+// the kernel waits for that peer's `ready` announcement of this epoch (made by the peer's first kernel of the call,
+// i.e. after everything of its previous call has drained); afterwards it releases one flag per peer and waits for
+// all of theirs.
+struct PeerGather {
+    PeerSeg seg[16];
+    int nseg;
+    int npeer;
+    unsigned *peer_flag[8];       // my slot in each peer's gather-flag array
+    const unsigned *my_flag[8];   // the peers' slots in mine
+    const unsigned *ready[8];     // the peers' ready slots in mine
+    unsigned epoch;
+    unsigned *done_counter;
+    unsigned *error_flag;
+};
+void launch_peer_gather(const PeerGather &g, cudaStream_t s);
 
 }  // namespace hbdist

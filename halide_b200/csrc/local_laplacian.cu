@@ -25,6 +25,7 @@ namespace {
 
 using namespace llk;
 
+int g_shard_coarse_level = 0;  // halide_b200_ll_shard_coarse_level: 0 auto, -1 exchange level by level, n >= 2 gather level n
 int g_force_naive = 0;  // test hook bitmask (halide_b200_ll_force_generic): 1 = generic down kernels, 2 = generic up, 4 = generic final
 
 const hb::ArgSpec kIn = {"input", halide_type_uint, 16, 3, false};
@@ -55,6 +56,7 @@ const halide_filter_metadata_t kMetaAuto = {1, 5, kArgs, "x86-64-linux-cuda-cuda
 
 // Everything one call needs on the device: frame description + per-level buffers.
 struct Plan {
+    bool interior = false;  // row-sharded: this launch covers only rows whose taps stay inside the band (no halo rows, no clamp at the band edge)
     LLFrame f;
     LevelSet ls;
     ll::Geom geom;
@@ -114,6 +116,7 @@ void fill_frame(Plan &p, halide_buffer_t *input, halide_buffer_t *output, void *
     f.out_sy = output->dim[1].stride; f.out_sc = output->dim[2].stride;
     f.out_x0 = output->dim[0].min; f.out_y0 = output->dim[1].min; f.out_c0 = output->dim[2].min;
     f.W = output->dim[0].extent; f.H = output->dim[1].extent; f.C = output->dim[2].extent;
+    f.row0 = f.out_y0; f.nrows = f.H;
     f.levels = levels;
     f.beta = beta;
     f.flm1 = (float)(levels - 1);
@@ -185,7 +188,7 @@ void launch_down(Plan &p, int j, cudaStream_t s) {  // produce level j (j >= 1) 
         if (fast) {
             size_t smem = (size_t)(2 * p.f.lut_half + 1) * sizeof(float);
             const int xb = strip_xblocks(lb[1]);
-            if (p.f.halo_top_rows || p.f.halo_bot_rows || p.f.clamp_y0 != p.f.in_y0 || p.f.clamp_h != p.f.in_h) {
+            if (!p.interior && (p.f.halo_top_rows || p.f.halo_bot_rows || p.f.clamp_y0 != p.f.in_y0 || p.f.clamp_h != p.f.in_h)) {
                 static int slots = strip_slots(ll_down_strip_kernel<8, true, true>, 16 * 1024);
                 HB_LAUNCH("ll_level1_strip", (ll_down_strip_kernel<8, true, true>), strip_grid(lb[1], slots), 128, smem, s, p.f,
                           lb[1], lb[1], xb);
@@ -232,8 +235,9 @@ void launch_up(Plan &p, int j, cudaStream_t s) {  // produce outGPyramid[j] (1 <
 
 void launch_final(Plan &p, cudaStream_t s) {
     LevelBuf *lb = p.ls.lv;
+    if (p.f.nrows <= 0) return;
     if (p.J > 1 && p.K == 8 && !(g_force_naive & 4) && p.f.C <= 3) {
-        dim3 g((p.f.W + kUpTW - 1) / kUpTW, (p.f.H + kUpTH - 1) / kUpTH);
+        dim3 g((p.f.W + kUpTW - 1) / kUpTW, (p.f.nrows + kUpTH - 1) / kUpTH);
         size_t smem = 513 * sizeof(float);
         if (p.f.io.wait_up[0] || p.f.io.wait_dn[0]) {
             HB_LAUNCH("ll_final_tile", (ll_up_tile_kernel<true, true>), g, 256, smem, s, p.f, lb[1], lb[1]);
@@ -241,7 +245,7 @@ void launch_final(Plan &p, cudaStream_t s) {
             HB_LAUNCH("ll_final_tile", (ll_up_tile_kernel<true, false>), g, 256, smem, s, p.f, lb[1], lb[1]);
         }
     } else {
-        HB_LAUNCH("ll_final", ll_final_naive_kernel, grid_for(p.f.W, p.f.H), kBlk, 0, s, p.f, lb[1], p.J > 1 ? 1 : 0);
+        HB_LAUNCH("ll_final", ll_final_naive_kernel, grid_for(p.f.W, p.f.nrows), kBlk, 0, s, p.f, lb[1], p.J > 1 ? 1 : 0);
     }
 }
 
@@ -322,12 +326,15 @@ struct SlabLayout {  // POD, exchanged between ranks
     int halo_top_rows, halo_bot_rows;
     cudaIpcMemHandle_t handle;
 };
+constexpr int kMaxPeers = 8;  // flag slots per rank (one NVSwitch domain)
 struct ShardPlan {
-    int key[10];
+    int key[12];
     bool valid = false;
     char *slab = nullptr;
     SlabLayout mine, up, dn;
     char *up_base = nullptr, *dn_base = nullptr;
+    std::vector<SlabLayout> all;  // every rank's layout, rank order
+    std::vector<char *> base;     // every rank's slab mapped here (null for this rank and for unmapped ranks)
     unsigned epoch = 0;
     unsigned *host_error = nullptr, *dev_error = nullptr;  // mapped pinned: set by a timed-out wait
 };
@@ -336,15 +343,16 @@ ShardPlan g_shard;
 void destroy_shard_plan() {
     if (!g_shard.valid) return;
     cudaDeviceSynchronize();
-    if (g_shard.up_base) cudaIpcCloseMemHandle(g_shard.up_base);
-    if (g_shard.dn_base) cudaIpcCloseMemHandle(g_shard.dn_base);
+    for (char *b : g_shard.base) {
+        if (b) cudaIpcCloseMemHandle(b);
+    }
     if (g_shard.slab) cudaFree(g_shard.slab);
     if (g_shard.host_error) cudaFreeHost(g_shard.host_error);
     g_shard = ShardPlan();
 }
 
 // Collective: every rank must call it with its own geometry at the same point of the program.
-int build_shard_plan(const Plan &p, const int *key, bool first, bool last) {
+int build_shard_plan(const Plan &p, const int *key, bool first, bool last, bool map_all) {
     destroy_shard_plan();
     ShardPlan &sp = g_shard;
     SlabLayout &L = sp.mine;
@@ -355,7 +363,9 @@ int build_shard_plan(const Plan &p, const int *key, bool first, bool last) {
         off += (bytes + 255) & ~255ull;
         return o;
     };
-    L.flags = take(256);  // [step*2 + dir] epochs, then the done counter at word 48
+    // words 0..31: [step*2 + dir] halo epochs; 32..39: gather epochs by source rank; 40..47: ready epochs by source
+    // rank; 48: the done counter
+    L.flags = take(256);
     L.lut = take((2ull * p.f.lut_half + 1) * sizeof(float));
     L.halo_top_rows = first ? 0 : 1;
     L.halo_bot_rows = last ? 0 : 2;
@@ -388,22 +398,26 @@ int build_shard_plan(const Plan &p, const int *key, bool first, bool last) {
     *sp.host_error = 0;
     cudaDeviceSynchronize();
     const int n = hbdist::size(), me = hbdist::rank();
-    std::vector<SlabLayout> all(n);
-    int r = hbdist::allgather_bytes(&L, all.data(), sizeof(SlabLayout));
+    sp.all.assign(n, SlabLayout());
+    int r = hbdist::allgather_bytes(&L, sp.all.data(), sizeof(SlabLayout));
     if (r) return r;
-    if (!first) {
-        sp.up = all[me - 1];
-        if (cudaIpcOpenMemHandle((void **)&sp.up_base, sp.up.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+    sp.base.assign(n, nullptr);
+    for (int q = 0; q < n; q++) {
+        // neighbours always; everybody when a level is gathered all-to-all (map_all)
+        if (q == me || !(map_all || q == me - 1 || q == me + 1)) continue;
+        if (cudaIpcOpenMemHandle((void **)&sp.base[q], sp.all[q].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
             cudaGetLastError();
-            return hb::fail(halide_error_code_generic_error, "local_laplacian_sharded: cannot map rank %d's slab (no peer access?)", me - 1);
+            sp.base[q] = nullptr;
+            return hb::fail(halide_error_code_generic_error, "local_laplacian_sharded: cannot map rank %d's slab (no peer access?)", q);
         }
     }
+    if (!first) {
+        sp.up = sp.all[me - 1];
+        sp.up_base = sp.base[me - 1];
+    }
     if (!last) {
-        sp.dn = all[me + 1];
-        if (cudaIpcOpenMemHandle((void **)&sp.dn_base, sp.dn.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-            cudaGetLastError();
-            return hb::fail(halide_error_code_generic_error, "local_laplacian_sharded: cannot map rank %d's slab (no peer access?)", me + 1);
-        }
+        sp.dn = sp.all[me + 1];
+        sp.dn_base = sp.base[me + 1];
     }
     memcpy(sp.key, key, sizeof(sp.key));
     sp.valid = true;
@@ -468,7 +482,32 @@ int run_local_laplacian_sharded(halide_buffer_t *input, int levels, float alpha,
     ll::Geom whole = ll::make_geom(outx, frame_y, inx, frame_y, p.J);
     ll::BandLevel bl[ll::kMaxJ];
     ll::compute_band_y(whole, band, first, last, bl);
-    for (int j = 1; j < p.J; j++) {
+    static const bool use_peer = [] {
+        const char *e = getenv("HALIDE_B200_HALO");
+        return !(e && strcmp(e, "nccl") == 0);
+    }();
+    // Coarse replication: levels jr.. are tiny, so exchanging their halos level by level costs one NVLink flag round
+    // trip per level and sweep with nothing to hide it behind.  Instead every rank's band of level jr is gathered
+    // all-to-all once, and levels jr+1.. (down) and ..jr (up) are computed redundantly for the whole frame on every
+    // rank.  jr = the first level whose gather traffic per rank is at most 12 MiB; it depends only on the frame and the rank
+    // count, so all ranks agree.  jr == J: no replication (level-by-level exchange).
+    int jr = p.J;
+    if (use_peer && nranks >= 2 && nranks <= kMaxPeers && g_shard_coarse_level >= 0 && p.J >= 4) {
+        if (g_shard_coarse_level > 0) {
+            jr = g_shard_coarse_level < 2 ? 2 : (g_shard_coarse_level > p.J - 1 ? p.J - 1 : g_shard_coarse_level);
+        } else {
+            jr = p.J - 1;
+            for (int j = 2; j < p.J - 1; j++) {
+                const unsigned long long rows = (unsigned long long)(whole.lv[j].sy.n() + nranks - 1) / nranks;
+                // measured (4K band per GPU): one more level in the sharded sweeps costs ~40 us, 5 MB of gather ~5 us
+                if (rows * whole.lv[j].gpitch * (p.K + 1) * sizeof(float) * (nranks - 1) <= (12ull << 20)) {
+                    jr = j;
+                    break;
+                }
+            }
+        }
+    }
+    for (int j = 1; j < p.J && j <= jr; j++) {
         if (bl[j].own.n() < 2 || bl[j].own_o.n() < 1) {
             return hb::fail(halide_error_code_constraint_violated,
                             "local_laplacian_sharded: band of %d rows is too small for %d pyramid levels (level %d owns %d rows)",
@@ -476,20 +515,21 @@ int run_local_laplacian_sharded(halide_buffer_t *input, int levels, float alpha,
         }
     }
     p.geom = ll::make_band_geom(whole, bl);
+    if (jr < p.J) {
+        // levels jr.. are held for the whole frame; level jr's rows are produced band by band (cy) and gathered
+        for (int j = jr; j < p.J; j++) p.geom.lv[j] = whole.lv[j];
+        p.geom.lv[jr].cy = bl[jr].own;
+    }
     p.f.clamp_y0 = frame_y.lo;
     p.f.clamp_h = frame_y.n();
-    static const bool use_peer = [] {
-        const char *e = getenv("HALIDE_B200_HALO");
-        return !(e && strcmp(e, "nccl") == 0);
-    }();
     cudaStream_t s = hb::stream();
     const int up = rank - 1, dn = rank + 1;
     const int C = p.f.in_c;
     if (use_peer) {
         // ---- peer-memory path: slab + IPC plan (built collectively on first use / geometry change) ----
-        const int key[10] = {W, p.f.in_w, band.lo, band.hi, frame_y.lo, frame_y.hi, rank, nranks, C, (int)(p.f.in_sy & 0x7fffffff)};
+        const int key[12] = {W, p.f.in_w, band.lo, band.hi, frame_y.lo, frame_y.hi, rank, nranks, C, (int)(p.f.in_sy & 0x7fffffff), jr, 0};
         if (!g_shard.valid || memcmp(g_shard.key, key, sizeof(key)) != 0) {
-            if ((r = build_shard_plan(p, key, first, last))) return r;
+            if ((r = build_shard_plan(p, key, first, last, jr < p.J))) return r;
         }
         ShardPlan &sp = g_shard;
         if (*sp.host_error) {
@@ -550,61 +590,191 @@ int run_local_laplacian_sharded(halide_buffer_t *input, int levels, float alpha,
             }
             // push only: the level-1 kernel's boundary blocks acquire the step-0 flags themselves (PeerIO)
             x.my_flag[0] = x.my_flag[1] = nullptr;
+            if (jr < p.J) {
+                // this kernel runs after everything of the previous call: tell every rank its level-jr rows may be overwritten
+                for (int q = 0; q < nranks; q++) {
+                    if (q != rank) x.ready_flag[x.nready++] = (unsigned *)(sp.base[q] + sp.all[q].flags) + 40 + rank;
+                }
+            }
             end_step();
             launch_lut(p, s);
             LevelBuf *lb = p.ls.lv;
             // From here on there are no exchange kernels: producers mirror their boundary rows into the neighbours'
             // slabs and release the step's flag, consumers acquire the flags of the halo rows they read (PeerIO).
             // Flag slots: down-sweep level j = step j; up-sweep level j = step 15 - j.
+            // A sharded sweep step is one launch of the sharded kernel variant over the band's rows: the blocks that hold the
+            // band's first / last rows acquire the neighbour's flag of the previous step before reading its halo rows, mirror the
+            // boundary rows they produce into the neighbour's slab, and the launch's last block releases the neighbour's flag of
+            // this step; interior blocks never wait.  (HALIDE_B200_SHARD_SPLIT=1 issues the interior rows with the single-GPU
+            // kernel variant and the edge rows as separate small launches instead — measured slower: the edge launches
+            // serialise behind the interior one.)
+            static const bool split = [] {
+                const char *e = getenv("HALIDE_B200_SHARD_SPLIT");
+                return e && e[0] == '1';
+            }();
             auto io_begin = [&]() {
                 memset(&p.f.io, 0, sizeof(p.f.io));
                 p.f.io.epoch = sp.epoch;
                 p.f.io.error_flag = sp.dev_error;
                 p.f.io.done_counter = flags + 48;
             };
-            int nwait = 0;
-            auto io_wait = [&](int st) {  // the neighbours' rows of step st must have landed (at most two steps per kernel)
-                if (!first) p.f.io.wait_up[nwait] = flags + st * 2 + 0;
-                if (!last) p.f.io.wait_dn[nwait] = flags + st * 2 + 1;
-                nwait++;
-            };
-            auto io_produce = [&](int st, const unsigned long long *up_a, const unsigned long long *up_b, const unsigned long long *dn_a,
-                                  const unsigned long long *dn_b, int j, size_t rb_a, size_t rb_b, int own_lo, int own_hi, int up_lo,
-                                  int dn_lo) {
-                if (!first) {
-                    p.f.io.up_a = sp.up_base + up_a[j] + (size_t)(own_lo - up_lo) * rb_a;
-                    p.f.io.up_b = up_b ? sp.up_base + up_b[j] + (size_t)(own_lo - up_lo) * rb_b : nullptr;
-                    p.f.io.up_flag = (unsigned *)(sp.up_base + sp.up.flags) + st * 2 + 1;
+            auto io_clear = [&]() { memset(&p.f.io, 0, sizeof(p.f.io)); };
+            // down-sweep level j: rows cy of lb[j] from level j-1 (step j-1 halos); `produce`: mirror to the neighbours (step j)
+            auto down_level = [&](int j, bool produce) {
+                const LevelBuf full = lb[j];
+                const Span cy = full.cy;
+                const size_t rb_a = (size_t)full.gpitch * p.K * sizeof(float), rb_b = (size_t)full.gpitch * sizeof(float);
+                auto io_top = [&]() {
+                    p.f.io.wait_up[0] = flags + (j - 1) * 2 + 0;
+                    if (produce) {
+                        p.f.io.up_a = sp.up_base + sp.up.gp[j] + (size_t)(cy.lo - sp.up.sy_lo[j]) * rb_a;
+                        p.f.io.up_b = sp.up_base + sp.up.ing[j] + (size_t)(cy.lo - sp.up.sy_lo[j]) * rb_b;
+                        p.f.io.up_flag = (unsigned *)(sp.up_base + sp.up.flags) + j * 2 + 1;
+                    }
+                };
+                auto io_bot = [&]() {
+                    p.f.io.wait_dn[0] = flags + (j - 1) * 2 + 1;
+                    if (produce) {
+                        p.f.io.dn_a = sp.dn_base + sp.dn.gp[j] + (size_t)(cy.hi - sp.dn.sy_lo[j]) * rb_a;
+                        p.f.io.dn_b = sp.dn_base + sp.dn.ing[j] + (size_t)(cy.hi - sp.dn.sy_lo[j]) * rb_b;
+                        p.f.io.dn_flag = (unsigned *)(sp.dn_base + sp.dn.flags) + j * 2 + 0;
+                    }
+                };
+                if (!split) {
+                    io_begin();
+                    if (!first) io_top();
+                    if (!last) io_bot();
+                    launch_down(p, j, s);
+                    io_clear();
+                    return;
                 }
-                if (!last) {
-                    p.f.io.dn_a = sp.dn_base + dn_a[j] + (size_t)(own_hi - dn_lo) * rb_a;
-                    p.f.io.dn_b = dn_b ? sp.dn_base + dn_b[j] + (size_t)(own_hi - dn_lo) * rb_b : nullptr;
-                    p.f.io.dn_flag = (unsigned *)(sp.dn_base + sp.dn.flags) + st * 2 + 0;
-                }
-            };
-            for (int j = 1; j < p.J; j++) {
-                io_begin();
-                nwait = 0;
-                io_wait(j - 1);  // level j-1 halo rows (step 0 = the input rows for level 1)
-                io_produce(j, sp.up.gp, sp.up.ing, sp.dn.gp, sp.dn.ing, j, (size_t)lb[j].gpitch * p.K * sizeof(float),
-                           (size_t)lb[j].gpitch * sizeof(float), lb[j].cy.lo, lb[j].cy.hi, sp.up.sy_lo[j], sp.dn.sy_lo[j]);
+                const int top_n = first ? 0 : (cy.n() < 2 ? cy.n() : 2);    // rows cy.lo, cy.lo+1: read 1 halo row, mirrored up
+                const int bot_n = last ? 0 : (cy.n() - top_n < 1 ? 0 : 1);  // row cy.hi: reads 2 halo rows, mirrored down
+                io_clear();
+                p.interior = true;
+                lb[j].cy = {cy.lo + top_n, cy.hi - bot_n};
                 launch_down(p, j, s);
-            }
-            for (int j = p.J - 1; j >= 1; j--) {
-                io_begin();
-                nwait = 0;
-                if (j < p.J - 1) {
-                    io_wait(j + 1);         // gPyramid[j+1] halo rows (only level J-1's have not been waited for yet)
-                    io_wait(15 - (j + 1));  // outGPyramid[j+1] halo rows
+                p.interior = false;
+                if (top_n) {
+                    io_begin();
+                    io_top();
+                    lb[j].cy = {cy.lo, cy.lo + top_n - 1};
+                    launch_down(p, j, s);
                 }
-                io_produce(15 - j, sp.up.outg, nullptr, sp.dn.outg, nullptr, j, (size_t)lb[j].opitch * sizeof(float), 0, lb[j].coy.lo,
-                           lb[j].coy.hi, sp.up.oy_lo[j], sp.dn.oy_lo[j]);
-                launch_up(p, j, s);
+                if (bot_n) {
+                    io_begin();
+                    io_bot();
+                    lb[j].cy = {cy.hi, cy.hi};
+                    launch_down(p, j, s);
+                }
+                lb[j] = full;
+                io_clear();
+            };
+            // up-sweep level j (j >= 1) or the final kernel (j == 0): `wait`: the coarse level's halo rows come from the
+            // neighbours (steps j+1 and 15-(j+1)); level j >= 1 mirrors its first / last row of outGPyramid[j] (step 15-j)
+            auto up_level = [&](int j, bool wait) {
+                const LevelBuf full = lb[j];
+                const Span rows = j ? full.coy : Span{p.f.out_y0, p.f.out_y0 + p.f.H - 1};
+                const size_t rb = (size_t)full.opitch * sizeof(float);
+                auto launch_rows = [&](Span r) {
+                    if (j) {
+                        lb[j].coy = r;
+                        launch_up(p, j, s);
+                    } else {
+                        p.f.row0 = r.lo;
+                        p.f.nrows = r.n();
+                        launch_final(p, s);
+                    }
+                };
+                auto io_top = [&]() {
+                    if (wait) {
+                        p.f.io.wait_up[0] = flags + (j + 1) * 2 + 0;
+                        p.f.io.wait_up[1] = flags + (15 - (j + 1)) * 2 + 0;
+                    }
+                    if (j) {
+                        p.f.io.up_a = sp.up_base + sp.up.outg[j] + (size_t)(rows.lo - sp.up.oy_lo[j]) * rb;
+                        p.f.io.up_flag = (unsigned *)(sp.up_base + sp.up.flags) + (15 - j) * 2 + 1;
+                    }
+                };
+                auto io_bot = [&]() {
+                    if (wait) {
+                        p.f.io.wait_dn[0] = flags + (j + 1) * 2 + 1;
+                        p.f.io.wait_dn[1] = flags + (15 - (j + 1)) * 2 + 1;
+                    }
+                    if (j) {
+                        p.f.io.dn_a = sp.dn_base + sp.dn.outg[j] + (size_t)(rows.hi - sp.dn.oy_lo[j]) * rb;
+                        p.f.io.dn_flag = (unsigned *)(sp.dn_base + sp.dn.flags) + (15 - j) * 2 + 0;
+                    }
+                };
+                if (!split) {
+                    io_begin();
+                    if (!first) io_top();
+                    if (!last) io_bot();
+                    launch_rows(rows);
+                } else {
+                    const int top_n = first ? 0 : (rows.n() < kUpTH ? rows.n() : kUpTH);
+                    const int bot_n = last ? 0 : (rows.n() - top_n < kUpTH ? rows.n() - top_n : kUpTH);
+                    io_clear();
+                    launch_rows({rows.lo + top_n, rows.hi - bot_n});
+                    if (top_n) {
+                        io_begin();
+                        io_top();
+                        launch_rows({rows.lo, rows.lo + top_n - 1});
+                    }
+                    if (bot_n) {
+                        io_begin();
+                        io_bot();
+                        launch_rows({rows.hi - bot_n + 1, rows.hi});
+                    }
+                }
+                lb[j] = full;
+                p.f.row0 = p.f.out_y0;
+                p.f.nrows = p.f.H;
+                io_clear();
+            };
+            const int jd = jr < p.J ? jr : p.J - 1;  // last level of the sharded down sweep
+            for (int j = 1; j <= jd; j++) down_level(j, j < jr);  // (level jr is gathered all-to-all instead of mirrored)
+            int ju = p.J - 1;  // first level of the sharded up sweep
+            if (jr < p.J) {
+                // ---- gather level jr, then the coarse tail for the whole frame on every rank (no communication) ----
+                hbdist::PeerGather g;
+                memset(&g, 0, sizeof(g));
+                g.epoch = sp.epoch;
+                g.done_counter = flags + 48;
+                g.error_flag = sp.dev_error;
+                const size_t row_off = (size_t)(lb[jr].cy.lo - lb[jr].sy.lo) * lb[jr].gpitch;  // same rows, same pitch on every rank
+                const size_t npx = (size_t)lb[jr].cy.n() * lb[jr].gpitch;
+                for (int q = 0; q < nranks; q++) {
+                    if (q == rank) continue;
+                    char *qb = sp.base[q];
+                    g.seg[g.nseg++] = {lb[jr].gp + row_off * p.K, qb + sp.all[q].gp[jr] + row_off * p.K * sizeof(float),
+                                       (unsigned)(npx * p.K * sizeof(float)), 16};
+                    g.seg[g.nseg++] = {lb[jr].ing + row_off, qb + sp.all[q].ing[jr] + row_off * sizeof(float),
+                                       (unsigned)(npx * sizeof(float)), 16};
+                    g.peer_flag[g.npeer] = (unsigned *)(qb + sp.all[q].flags) + 32 + rank;
+                    g.my_flag[g.npeer] = flags + 32 + q;
+                    g.ready[g.npeer] = flags + 40 + q;
+                    g.npeer++;
+                }
+                hbdist::launch_peer_gather(g, s);
+                memset(&p.f.io, 0, sizeof(p.f.io));
+                lb[jr].cy = lb[jr].sy;  // from here on level jr is complete
+                int j0 = p.J - 1;
+                if (!(g_force_naive & 8)) {
+                    while (j0 > jr && (int64_t)lb[j0].sx.n() * lb[j0].sy.n() <= 40 * 1024) j0--;
+                }
+                bool fused = false;
+                for (int j = jr + 1; j <= j0; j++) launch_down(p, j, s);
+                if (j0 < p.J - 1) fused = launch_coarse_fused(p, j0, s);
+                if (!fused) {
+                    for (int j = j0 + 1; j < p.J; j++) launch_down(p, j, s);
+                    for (int j = p.J - 1; j > j0; j--) launch_up(p, j, s);
+                }
+                for (int j = j0; j >= jr; j--) launch_up(p, j, s);
+                ju = jr - 1;
             }
-            io_begin();
-            nwait = 0;
-            io_wait(14);  // outGPyramid[1] halo rows
-            launch_final(p, s);
+            // the coarse level's halo rows are local when it is the gathered level; the final kernel (j == 0) reads level 1's
+            for (int j = ju; j >= 0; j--) up_level(j, j < p.J - 1 && j + 1 < jr);
             memset(&p.f.io, 0, sizeof(p.f.io));
         }
     } else {
@@ -714,6 +884,13 @@ extern "C" const halide_filter_metadata_t *local_laplacian_auto_schedule_metadat
 // Test hook: route K == 8 calls through the generic (any `levels`) kernels so both paths stay covered.
 extern "C" void halide_b200_ll_force_generic(int enable) {
     g_force_naive = enable;
+}
+
+// Row-sharded path: which pyramid level is gathered all-to-all (see run_local_laplacian_sharded).  Collective
+// setting: every rank must use the same value.  0 = choose by size (default), -1 = never (exchange halos level by
+// level), n >= 2 = level n.
+extern "C" void halide_b200_ll_shard_coarse_level(int level) {
+    g_shard_coarse_level = level;
 }
 
 // Row-sharded entry point (B200 extension; see run_local_laplacian_sharded).

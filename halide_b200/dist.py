@@ -5,6 +5,7 @@ bench.py); the data-path exchange — one ncclGroup of point-to-point halo messa
 — is issued by libhalide_b200.so on its compute stream (halide_b200/csrc/hb_dist.cu).
 """
 import ctypes
+import os
 
 from .lib import lib, check
 
@@ -59,6 +60,9 @@ class RowSharder:
         self.frame_h = band_h * world
         self.lo, self.hi = band_rows(rank, world, self.frame_h)
         init_from_torch_distributed()
+        lvl = os.environ.get("HALIDE_B200_SHARD_COARSE_LEVEL")  # experiment knob; see halide_b200_ll_shard_coarse_level
+        if lvl is not None:
+            lib.halide_b200_ll_shard_coarse_level(int(lvl))
 
     def set_band_mins(self, buf):
         """Put a band buffer (rows 0..band_h-1 locally) at its rows of the frame."""

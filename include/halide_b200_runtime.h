@@ -280,6 +280,10 @@ int halide_b200_local_laplacian_sharded(struct halide_buffer_t *input, int32_t l
 /* Host-only probe of the band geometry (rows owned / held per pyramid level) for tests; out[64]. */
 int halide_b200_ll_band_geometry(int32_t frame_w, int32_t frame_h, int32_t band_lo, int32_t band_hi, int32_t first,
                                  int32_t last, int32_t *out);
+/* Row-sharded local_laplacian: pyramid level gathered all-to-all so that the coarser levels are computed
+ * redundantly on every rank without further exchange.  0 = chosen by size (default), -1 = never (halos exchanged
+ * level by level), n >= 2 = level n.  Collective setting: all ranks must agree. */
+void halide_b200_ll_shard_coarse_level(int level);
 /* Test hook: bitmask routing levels==8 calls through the generic kernels (1 down, 2 up, 4 final,
  * 8 no fused coarse launch) so both code paths stay covered by the parity tests. */
 void halide_b200_ll_force_generic(int mask);

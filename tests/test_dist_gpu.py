@@ -21,6 +21,6 @@ def test_sharded_local_laplacian_matches_single_gpu(world, w, band_h):
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", "29531", os.path.join(ROOT, "tools", "dist_check.py"), str(w), str(band_h)]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "mismatches=0" in out.stdout

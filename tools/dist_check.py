@@ -34,12 +34,22 @@ def main():
     band_in = np.ascontiguousarray(frame[:, sh.lo:sh.hi + 1, :])
     band_out = np.zeros_like(band_in)
     b_in, b_out = HalideBuffer.from_numpy(band_in), HalideBuffer.from_numpy(band_out, host_dirty=False)
-    for _ in range(2):  # twice: the second call reuses pooled scratch
-        b_in.set_host_dirty(True)
-        sh.local_laplacian(b_in, 8, 1.0 / 7.0, 1.0, b_out)
-        b_out.copy_to_host()
     want = full_out[:, sh.lo:sh.hi + 1, :]
-    bad = int((band_out != want).sum())
+    bad = 0
+    # coarse-level modes: level-by-level halo exchange (-1), gather level chosen by size (0), forced gather levels
+    modes = [int(m) for m in os.environ.get("DIST_CHECK_MODES", "-1,0,2,3,6").split(",")]
+    for mode in modes:
+        halide_b200.capi.halide_b200_ll_shard_coarse_level(mode)
+        for it in range(3):  # repeated: pooled scratch, epochs, ready/gather handshakes of consecutive calls
+            band_out[:] = 0
+            b_in.set_host_dirty(True)
+            sh.local_laplacian(b_in, 8, 1.0 / 7.0, 1.0, b_out)
+            b_out.copy_to_host()
+            n = int((band_out != want).sum())
+            if n:
+                print(f"rank {rank}: mode {mode} call {it}: {n} mismatching samples", flush=True)
+            bad += n
+    halide_b200.capi.halide_b200_ll_shard_coarse_level(0)
     t = torch.tensor([bad], device="cuda")
     td.all_reduce(t)
     if rank == 0:
