@@ -441,6 +441,19 @@ void bind_slab(Plan &p) {  // point the plan's buffers into the slab
     p.ls.lv[0] = p.ls.lv[1];
 }
 
+// Row-sharded path: the level gathered all-to-all (levels above it are replicated on every rank), or J for none.
+// Depends only on the whole frame's geometry and the rank count, so every rank computes the same value.
+int choose_coarse_level(const ll::Geom &whole, int nranks, int J, int K) {
+    if (nranks < 2 || nranks > kMaxPeers || g_shard_coarse_level < 0 || J < 4) return J;
+    if (g_shard_coarse_level > 0) return g_shard_coarse_level < 2 ? 2 : (g_shard_coarse_level > J - 1 ? J - 1 : g_shard_coarse_level);
+    for (int j = 2; j < J - 1; j++) {
+        const unsigned long long rows = (unsigned long long)(whole.lv[j].sy.n() + nranks - 1) / nranks;
+        // measured (4K band per GPU): one more level in the sharded sweeps costs ~40 us, 5 MB of gather ~5 us
+        if (rows * whole.lv[j].gpitch * (K + 1) * sizeof(float) * (nranks - 1) <= (12ull << 20)) return j;
+    }
+    return J - 1;
+}
+
 // ---- row-sharded variant (one process per GPU) -----------------------------------------------------------
 // `input`/`output` describe this rank's band: all columns and channels of the frame, rows
 // [dim[1].min, dim[1].min + extent) in the frame's coordinates.  frame_y_min/extent give the rows of the whole
@@ -491,22 +504,7 @@ int run_local_laplacian_sharded(halide_buffer_t *input, int levels, float alpha,
     // all-to-all once, and levels jr+1.. (down) and ..jr (up) are computed redundantly for the whole frame on every
     // rank.  jr = the first level whose gather traffic per rank is at most 12 MiB; it depends only on the frame and the rank
     // count, so all ranks agree.  jr == J: no replication (level-by-level exchange).
-    int jr = p.J;
-    if (use_peer && nranks >= 2 && nranks <= kMaxPeers && g_shard_coarse_level >= 0 && p.J >= 4) {
-        if (g_shard_coarse_level > 0) {
-            jr = g_shard_coarse_level < 2 ? 2 : (g_shard_coarse_level > p.J - 1 ? p.J - 1 : g_shard_coarse_level);
-        } else {
-            jr = p.J - 1;
-            for (int j = 2; j < p.J - 1; j++) {
-                const unsigned long long rows = (unsigned long long)(whole.lv[j].sy.n() + nranks - 1) / nranks;
-                // measured (4K band per GPU): one more level in the sharded sweeps costs ~40 us, 5 MB of gather ~5 us
-                if (rows * whole.lv[j].gpitch * (p.K + 1) * sizeof(float) * (nranks - 1) <= (12ull << 20)) {
-                    jr = j;
-                    break;
-                }
-            }
-        }
-    }
+    const int jr = use_peer ? choose_coarse_level(whole, nranks, p.J, p.K) : p.J;
     for (int j = 1; j < p.J && j <= jr; j++) {
         if (bl[j].own.n() < 2 || bl[j].own_o.n() < 1) {
             return hb::fail(halide_error_code_constraint_violated,
@@ -891,6 +889,13 @@ extern "C" void halide_b200_ll_force_generic(int enable) {
 // level), n >= 2 = level n.
 extern "C" void halide_b200_ll_shard_coarse_level(int level) {
     g_shard_coarse_level = level;
+}
+
+// Probe for the CPU-side tests (no CUDA calls): the level halide_b200_local_laplacian_sharded would gather for a
+// frame of frame_w x frame_h split over nranks ranks, or 8 when halos are exchanged level by level.
+extern "C" int halide_b200_ll_shard_plan_level(int32_t frame_w, int32_t frame_h, int32_t nranks) {
+    Span fx = {0, frame_w - 1}, fy = {0, frame_h - 1};
+    return choose_coarse_level(ll::make_geom(fx, fy, fx, fy, ll::kMaxJ), nranks, ll::kMaxJ, 8);
 }
 
 // Row-sharded entry point (B200 extension; see run_local_laplacian_sharded).

@@ -284,6 +284,8 @@ int halide_b200_ll_band_geometry(int32_t frame_w, int32_t frame_h, int32_t band_
  * redundantly on every rank without further exchange.  0 = chosen by size (default), -1 = never (halos exchanged
  * level by level), n >= 2 = level n.  Collective setting: all ranks must agree. */
 void halide_b200_ll_shard_coarse_level(int level);
+/* The level the sharded call would gather for a frame_w x frame_h frame over nranks ranks (8 = none); host-only. */
+int halide_b200_ll_shard_plan_level(int32_t frame_w, int32_t frame_h, int32_t nranks);
 /* Test hook: bitmask routing levels==8 calls through the generic kernels (1 down, 2 up, 4 final,
  * 8 no fused coarse launch) so both code paths stay covered by the parity tests. */
 void halide_b200_ll_force_generic(int mask);
