@@ -448,8 +448,9 @@ int choose_coarse_level(const ll::Geom &whole, int nranks, int J, int K) {
     if (g_shard_coarse_level > 0) return g_shard_coarse_level < 2 ? 2 : (g_shard_coarse_level > J - 1 ? J - 1 : g_shard_coarse_level);
     for (int j = 2; j < J - 1; j++) {
         const unsigned long long rows = (unsigned long long)(whole.lv[j].sy.n() + nranks - 1) / nranks;
-        // measured (4K band per GPU): one more level in the sharded sweeps costs ~40 us, 5 MB of gather ~5 us
-        if (rows * whole.lv[j].gpitch * (K + 1) * sizeof(float) * (nranks - 1) <= (12ull << 20)) return j;
+        // measured at N=2 (4K band per GPU): gathering level 3 (4.7 MB per peer) 312-326 us, level 4 (1.2 MB) 315-316 us,
+        // level 5 359 us: one more level in the sharded sweeps costs ~40 us, the bytes hardly matter at this size
+        if (rows * whole.lv[j].gpitch * (K + 1) * sizeof(float) <= (5ull << 18)) return j;  // <= 1.25 MiB per peer
     }
     return J - 1;
 }
@@ -502,7 +503,7 @@ int run_local_laplacian_sharded(halide_buffer_t *input, int levels, float alpha,
     // Coarse replication: levels jr.. are tiny, so exchanging their halos level by level costs one NVLink flag round
     // trip per level and sweep with nothing to hide it behind.  Instead every rank's band of level jr is gathered
     // all-to-all once, and levels jr+1.. (down) and ..jr (up) are computed redundantly for the whole frame on every
-    // rank.  jr = the first level whose gather traffic per rank is at most 12 MiB; it depends only on the frame and the rank
+    // rank.  jr = the first level whose band is at most 1.25 MiB (what each peer receives); it depends only on the frame and the rank
     // count, so all ranks agree.  jr == J: no replication (level-by-level exchange).
     const int jr = use_peer ? choose_coarse_level(whole, nranks, p.J, p.K) : p.J;
     for (int j = 1; j < p.J && j <= jr; j++) {

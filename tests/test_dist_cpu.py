@@ -78,13 +78,13 @@ def test_gloo_world2_control_plane(tmp_path):
 
 def test_coarse_level_choice(hb):
     """The gathered level depends only on the frame and the rank count (every rank must pick the same one):
-    4K bands -> level 3 at N=2 (4.7 MB per rank), level 4 at N=4 / N=8; small frames gather level 2; more ranks
+    4K bands -> level 4 (1.2 MB per peer) at N=2, 4 and 8; smaller frames gather a finer level; more ranks
     than flag slots, or the -1 override, fall back to level-by-level exchange (8 = no gather)."""
     lvl = hb.capi.halide_b200_ll_shard_plan_level
-    assert lvl(3840, 2160 * 2, 2) == 3
+    assert lvl(3840, 2160 * 2, 2) == 4
     assert lvl(3840, 2160 * 4, 4) == 4
     assert lvl(3840, 2160 * 8, 8) == 4
-    assert lvl(1000, 1280, 2) == 2
+    assert lvl(1000, 1280, 2) == 3
     assert lvl(3840, 2160, 1) == 8
     assert lvl(3840, 2160 * 16, 16) == 8
     hb.capi.halide_b200_ll_shard_coarse_level(-1)
