@@ -26,7 +26,7 @@ namespace {
 using namespace llk;
 
 int g_shard_coarse_level = 0;  // halide_b200_ll_shard_coarse_level: 0 auto, -1 exchange level by level, n >= 2 gather level n
-int g_force_naive = 0;  // test hook bitmask (halide_b200_ll_force_generic): 1 = generic down kernels, 2 = generic up, 4 = generic final
+int g_force_naive = 0;  // test hook bitmask (halide_b200_ll_force_generic): 1 = generic down kernels, 2 = generic up, 4 = generic final, 8 = no fused coarse launch, 16 = general-layout final kernel
 
 const hb::ArgSpec kIn = {"input", halide_type_uint, 16, 3, false};
 const hb::ArgSpec kOut = {"output", halide_type_uint, 16, 3, true};
@@ -239,10 +239,23 @@ void launch_final(Plan &p, cudaStream_t s) {
     if (p.J > 1 && p.K == 8 && !(g_force_naive & 4) && p.f.C <= 3) {
         dim3 g((p.f.W + kUpTW - 1) / kUpTW, (p.f.nrows + kUpTH - 1) / kUpTH);
         size_t smem = 513 * sizeof(float);
-        if (p.f.io.wait_up[0] || p.f.io.wait_dn[0]) {
-            HB_LAUNCH("ll_final_tile", (ll_up_tile_kernel<true, true>), g, 256, smem, s, p.f, lb[1], lb[1]);
+        // the common layout takes the kernel's SIMPLE path (32-bit addressing, one aligned word per thread and channel)
+        const LLFrame &f = p.f;
+        const int64_t in_span = (int64_t)f.in_h * f.in_sy + 3 * f.in_sc, out_span = (int64_t)f.H * f.out_sy + 3 * f.out_sc;
+        const bool simple = f.C == 3 && f.in_c0 == 0 && f.out_c0 == 0 && f.in_c >= 3 && (f.W & 1) == 0 &&
+                            ((f.out_x0 - f.in_x0) & 1) == 0 && ((uintptr_t)f.in & 3) == 0 && ((uintptr_t)f.out & 3) == 0 &&
+                            (f.in_sy & 1) == 0 && (f.in_sc & 1) == 0 && (f.out_sy & 1) == 0 && (f.out_sc & 1) == 0 &&
+                            f.in_sy > 0 && f.in_sc > 0 && f.out_sy > 0 && f.out_sc > 0 && in_span < (1ll << 31) &&
+                            out_span < (1ll << 31) && !(g_force_naive & 16);
+        const bool peer = p.f.io.wait_up[0] || p.f.io.wait_dn[0];
+        if (peer && simple) {
+            HB_LAUNCH("ll_final_tile", (ll_up_tile_kernel<true, true, true>), g, 256, smem, s, p.f, lb[1], lb[1]);
+        } else if (peer) {
+            HB_LAUNCH("ll_final_tile", (ll_up_tile_kernel<true, true, false>), g, 256, smem, s, p.f, lb[1], lb[1]);
+        } else if (simple) {
+            HB_LAUNCH("ll_final_tile", (ll_up_tile_kernel<true, false, true>), g, 256, smem, s, p.f, lb[1], lb[1]);
         } else {
-            HB_LAUNCH("ll_final_tile", (ll_up_tile_kernel<true, false>), g, 256, smem, s, p.f, lb[1], lb[1]);
+            HB_LAUNCH("ll_final_tile", (ll_up_tile_kernel<true, false, false>), g, 256, smem, s, p.f, lb[1], lb[1]);
         }
     } else {
         HB_LAUNCH("ll_final", ll_final_naive_kernel, grid_for(p.f.W, p.f.nrows), kBlk, 0, s, p.f, lb[1], p.J > 1 ? 1 : 0);

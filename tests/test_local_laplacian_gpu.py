@@ -101,3 +101,29 @@ def test_generic_kernels_agree_with_fast_path(hb, oracle):
         l.halide_b200_ll_force_generic(0)
     got_fast = run_local_laplacian(hb, img, 8, 1.0 / 7.0, 1.0)
     assert np.array_equal(got_generic, want) and np.array_equal(got_fast, want)
+
+
+@pytest.mark.parametrize("shape", [(3, 130, 256), (3, 97, 198), (3, 64, 66)])
+def test_final_kernel_simple_and_general_layout_paths(hb, oracle, shape):
+    """Even-width 3-channel frames with 4-byte aligned rows take the final kernel's SIMPLE path (32-bit addressing,
+    one aligned word per thread and channel); hook bit 16 forces the general-layout path on the same frame.
+    Both must equal the oracle; a crop with odd column offsets must fall back to the general path by itself."""
+    img = u16_frame(shape, 77)
+    want = oracle.local_laplacian(img, 8, 1.0 / 7.0, 1.0)
+    l = hb.load_library()
+    got_simple = run_local_laplacian(hb, img, 8, 1.0 / 7.0, 1.0)
+    try:
+        l.halide_b200_ll_force_generic(16)
+        got_general = run_local_laplacian(hb, img, 8, 1.0 / 7.0, 1.0)
+    finally:
+        l.halide_b200_ll_force_generic(0)
+    assert np.array_equal(got_simple, want) and np.array_equal(got_general, want)
+    c, h, w = shape
+    out_shape = (3, h - 9, w - 12)  # even width, output columns start at an odd input column
+    want_crop = oracle.local_laplacian(img, 8, 1.0 / 7.0, 1.0, out_shape=out_shape, in_mins=(0, 0, 0), out_mins=(5, 4, 0))
+    got_crop = run_local_laplacian(hb, img, 8, 1.0 / 7.0, 1.0, out_shape=out_shape, in_mins=(0, 0, 0), out_mins=(5, 4, 0))
+    assert np.array_equal(got_crop, want_crop)
+    out_shape = (3, h - 8, w - 12)  # even offsets: SIMPLE path on a crop (row pointer no longer at the buffer start)
+    want_crop = oracle.local_laplacian(img, 8, 1.0 / 7.0, 1.0, out_shape=out_shape, in_mins=(0, 0, 0), out_mins=(6, 4, 0))
+    got_crop = run_local_laplacian(hb, img, 8, 1.0 / 7.0, 1.0, out_shape=out_shape, in_mins=(0, 0, 0), out_mins=(6, 4, 0))
+    assert np.array_equal(got_crop, want_crop)
