@@ -110,11 +110,12 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def recorded_traffic(workload):
+def recorded_traffic(workload, kernel):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(p)).get(workload)
+        v = json.load(open(p)).get(workload)
+        return v.get(kernel) if isinstance(v, dict) else v
     except Exception:
         return None
 
@@ -381,7 +382,7 @@ def run_ours(args, rank, world, local_rank):
             achieved = alg_bytes / avg_s / 1e9
             pipe_ms = sum(v[1] for v in rep.values()) / reps
             roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "traffic": recorded_traffic(args.workload), "peak_source": how,
+                        "frac": achieved / peak, "traffic": recorded_traffic(args.workload, name), "peak_source": how,
                         "kernel_ms": avg_s * 1e3, "algorithmic_bytes": alg_bytes,
                         "pipeline_kernel_ms": pipe_ms,
                         "pipeline_frac": alg_bytes / (pipe_ms / 1e3) / 1e9 / peak}
