@@ -21,7 +21,8 @@ class FramePipeline:
 
     ``submit`` returns a ticket; ``result(ticket)`` blocks until that call has finished (including whatever
     ``fn`` did to bring the result to the host) and re-raises its exception, if any.  Jobs submitted with the
-    same ``slot`` run on the same worker, in order — use one slot per set of buffers.
+    same ``slot`` run on the same worker, in order — use one slot per set of buffers.  ``device=None`` skips the
+    CUDA setup (workers run ``fn`` as is): for callers that bind streams themselves, and for the host-logic tests.
     """
 
     def __init__(self, depth=3, device=0):
@@ -38,16 +39,16 @@ class FramePipeline:
 
     def _worker(self, index, device):
         stream = None
-        try:
-            check(lib.halide_b200_set_device(device))
-            stream = lib.halide_b200_stream_create()
-            if not stream:
-                raise RuntimeError("halide_b200_stream_create failed")
-            lib.halide_b200_set_stream(stream)
-        except BaseException as e:  # surfaced on the first job
-            init_error = e
-        else:
-            init_error = None
+        init_error = None
+        if device is not None:
+            try:
+                check(lib.halide_b200_set_device(device))
+                stream = lib.halide_b200_stream_create()
+                if not stream:
+                    raise RuntimeError("halide_b200_stream_create failed")
+                lib.halide_b200_set_stream(stream)
+            except BaseException as e:  # surfaced on the first job
+                init_error = e
         q = self._queues[index]
         while True:
             job = q.get()
@@ -84,10 +85,13 @@ class FramePipeline:
         return val
 
     def close(self):
+        if self._threads is None:
+            return
         for q in self._queues:
             q.put(None)
         for t in self._threads:
             t.join()
+        self._threads = None
 
     def __enter__(self):
         return self
