@@ -92,3 +92,17 @@ def test_coarse_level_choice(hb):
     hb.capi.halide_b200_ll_shard_coarse_level(5)
     assert lvl(3840, 2160 * 2, 2) == 5
     hb.capi.halide_b200_ll_shard_coarse_level(0)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_input_halo_sharding_matches_whole_frame_oracle(world):
+    """SURVEY §8e for blur, nl_means, stencil_chain, bilateral_grid and camera_pipe: the sharding is host logic only
+    (halo rule, row exchange over torch.distributed, buffer placement by mins), so it is checked end to end on CPU —
+    gloo, CPU tensors, the oracle standing in for the single-GPU filter — against the oracle on the whole frame."""
+    port = 29518 + world
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                          "--master-addr", "127.0.0.1", "--master-port", str(port),
+                          os.path.join(ROOT, "tests", "dist_rows_worker.py")],
+                         capture_output=True, text=True, timeout=600, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert f"ROWS_CHECK world={world} failures=[]" in out.stdout

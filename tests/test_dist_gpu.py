@@ -24,3 +24,16 @@ def test_sharded_local_laplacian_matches_single_gpu(world, w, band_h):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "mismatches=0" in out.stdout
+
+
+def test_input_halo_filters_sharded_match_single_gpu():
+    """blur / nl_means / stencil_chain / bilateral_grid / camera_pipe row-sharded over 2 GPUs (NCCL row exchange +
+    the ordinary filter on the extended band) equal the whole-frame call on one GPU (bit for bit for the integer
+    pipelines, 1e-4 relative for the float ones)."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29532", os.path.join(ROOT, "tools", "dist_rows_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "mismatches=0" in out.stdout
