@@ -577,13 +577,6 @@ int run_local_laplacian_sharded(halide_buffer_t *input, int levels, float alpha,
             hbdist::launch_peer_exchange(x, s);
             step++;
         };
-        // rows of a row-major f32 array: my first n_up owned rows go up, my last owned row goes down
-        auto rows_f32 = [&](const float *mine, const unsigned long long *peer_off_up, const unsigned long long *peer_off_dn, int j,
-                            size_t row_elems, int my_lo, int own_lo, int own_hi, int up_lo, int dn_lo, int n_up) {
-            const size_t rb = row_elems * sizeof(float);
-            if (!first) add_seg(mine + (size_t)(own_lo - my_lo) * row_elems, sp.up_base + peer_off_up[j] + (size_t)(own_lo - up_lo) * rb, n_up * rb, 16);
-            if (!last) add_seg(mine + (size_t)(own_hi - my_lo) * row_elems, sp.dn_base + peer_off_dn[j] + (size_t)(own_hi - dn_lo) * rb, rb, 16);
-        };
         {
             hb::CallTimer timer(s);
             // step 0: input rows (per channel; rows may be strided in the caller's buffer -> one segment per row)
