@@ -26,7 +26,7 @@ namespace {
 using namespace llk;
 
 int g_shard_coarse_level = 0;  // halide_b200_ll_shard_coarse_level: 0 auto, -1 exchange level by level, n >= 2 gather level n
-int g_force_naive = 0;  // test hook bitmask (halide_b200_ll_force_generic): 1 = generic down kernels, 2 = generic up, 4 = generic final, 8 = no fused coarse launch, 16 = general-layout final kernel, 32 = experimental pair-column level-1 kernel
+int g_force_naive = 0;  // test hook bitmask (halide_b200_ll_force_generic): 1 = generic down kernels, 2 = generic up, 4 = generic final, 8 = no fused coarse launch, 16 = general-layout final kernel, 32 = pair-column level-1 kernel
 
 const hb::ArgSpec kIn = {"input", halide_type_uint, 16, 3, false};
 const hb::ArgSpec kOut = {"output", halide_type_uint, 16, 3, true};
@@ -191,7 +191,7 @@ void launch_down(Plan &p, int j, cudaStream_t s) {  // produce level j (j >= 1) 
             const bool sharded_rows = p.f.halo_top_rows || p.f.halo_bot_rows || p.f.clamp_y0 != p.f.in_y0 || p.f.clamp_h != p.f.in_h;
             if ((g_force_naive & 32) && !sharded_rows && p.f.in_sy > 0 && p.f.in_sc > 0 &&
                 (int64_t)p.f.in_h * p.f.in_sy + 3 * p.f.in_sc < (1ll << 31)) {
-                // EXPERIMENTAL two-columns-per-lane variant (see ll_level1_pair_kernel; not yet validated on hardware)
+                // alternative two-columns-per-lane variant (see ll_level1_pair_kernel: bit-exact, measured slightly slower)
                 const LLFrame &f = p.f;
                 const int wide = ((uintptr_t)f.in & 3) == 0 && (f.in_sy & 1) == 0 && (f.in_sc & 1) == 0 && (f.in_x0 & 1) == 0;
                 const int xbp = ((lb[1].sx.n() + kPairCols - 1) / kPairCols + 3) / 4;
