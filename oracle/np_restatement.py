@@ -1,0 +1,186 @@
+"""Second, independently structured restatement of two pipelines in numpy — TEST INFRASTRUCTURE ONLY.
+
+oracle/*.cpp evaluates the generators pixel by pixel through memoised recursive lambdas; this file evaluates the same
+Func definitions as whole-array float32 numpy expressions over explicitly inferred index ranges (the way Halide's
+bounds inference would size them).  Neither is the reference (which cannot be built here), but two
+restatements written differently that agree bit for bit make a mis-transcribed formula, tap or rounding order in the
+oracle much less likely.  tests/test_oracle_crosscheck.py compares them.
+
+Follows: apps/local_laplacian/local_laplacian_generator.cpp:19-87 (algorithm), :262-282 (downsample / upsample);
+src/IROperator.cpp:921-966 + :33-62 (halide_exp, evaluate_polynomial); src/Lerp.cpp:126-128 (lerp);
+apps/stencil_chain/stencil_chain_generator.cpp:17-30.  Halide semantics used: Euclidean integer / and %, float
+x / const -> x * fold(1/const), no FMA contraction, lerp(z, o, w) = z*(1-w) + o*w, clamp = max(min(a, hi), lo).
+"""
+import numpy as np
+
+F = np.float32
+
+
+class Field:
+    """A Func realised on the box x in [x0, x0+nx), y in [y0, y0+ny): arr[y - y0, x - x0(, k)]."""
+
+    def __init__(self, arr, x0, y0):
+        self.arr, self.x0, self.y0 = arr, x0, y0
+
+    def at(self, xs, ys):
+        xi, yi = np.asarray(xs) - self.x0, np.asarray(ys) - self.y0
+        assert xi.min() >= 0 and yi.min() >= 0 and xi.max() < self.arr.shape[1] and yi.max() < self.arr.shape[0], "read outside the realised box"
+        return self.arr[yi[:, None], xi[None, :]]
+
+
+def halide_exp(x_full):
+    x_full = x_full.astype(F)
+    ln2_part1, ln2_part2 = F(0.6931457519), F(1.4286067653e-6)
+    one_over_ln2 = F(1.0) / np.log(F(2.0), dtype=F)
+    scaled = x_full * one_over_ln2
+    k_real = np.floor(scaled)
+    k = k_real.astype(np.int32)
+    x = x_full - k_real * ln2_part1
+    x = x - k_real * ln2_part2
+    c = [F(v) for v in (0.00031965933071842413, 0.00119156835564003744, 0.00848988645943932717, 0.04160188091348320655,
+                        0.16667983794100929562, 0.49999899033463041098, 1.0, 1.0)]
+    x2 = x * x
+    even, odd = c[0], c[1]
+    for i in range(2, 8):
+        if i & 1:
+            odd = odd * x2 + c[i]
+        else:
+            even = even * x2 + c[i]
+    result = even * x + odd
+    biased = k + 127
+    two_to_the_n = (np.clip(biased, 0, 255).astype(np.uint32) << np.uint32(23)).view(F)
+    result = result * two_to_the_n
+    result = np.where(biased < 255, result, F(np.inf))
+    return np.where(biased > 0, result, F(0)).astype(F)
+
+
+def _down(f, xlo, xhi, ylo, yhi):
+    """downsample(f) on [xlo, xhi] x [ylo, yhi]: 1-3-3-1 in y, then in x (generator :266-272)."""
+    three, eighth = F(3.0), F(0.125)
+    xs_wide = np.arange(2 * xlo - 1, 2 * xhi + 3)
+    ys = np.arange(ylo, yhi + 1)
+    downy = (f.at(xs_wide, 2 * ys - 1) + three * (f.at(xs_wide, 2 * ys) + f.at(xs_wide, 2 * ys + 1)) + f.at(xs_wide, 2 * ys + 2)) * eighth
+    dy = Field(downy, 2 * xlo - 1, ylo)
+    xs = np.arange(xlo, xhi + 1)
+    downx = (dy.at(2 * xs - 1, ys) + three * (dy.at(2 * xs, ys) + dy.at(2 * xs + 1, ys)) + dy.at(2 * xs + 2, ys)) * eighth
+    return Field(downx.astype(F), xlo, ylo)
+
+
+def _lerp(zero, one, w):
+    return zero * (F(1.0) - w) + one * w
+
+
+def _up(f, xlo, xhi, ylo, yhi):
+    """upsample(f) on [xlo, xhi] x [ylo, yhi]: bilinear, x then y (generator :275-282); integer / and % are Euclidean."""
+    xs, ys = np.arange(xlo, xhi + 1), np.arange(ylo, yhi + 1)
+    cy = np.arange((ylo - 1) >> 1, ((yhi + 1) >> 1) + 1)  # coarse rows upy reads
+    wx = (((xs & 1) * 2 + 1).astype(F) * F(0.25))
+    wx = wx[None, :] if f.arr.ndim == 2 else wx[None, :, None]
+    upx = Field(_lerp(f.at((xs + 1) >> 1, cy), f.at((xs - 1) >> 1, cy), wx).astype(F), xlo, cy[0])
+    wy = (((ys & 1) * 2 + 1).astype(F) * F(0.25))
+    wy = wy[:, None] if f.arr.ndim == 2 else wy[:, None, None]
+    upy = _lerp(upx.at(xs, (ys + 1) >> 1), upx.at(xs, (ys - 1) >> 1), wy)
+    return Field(upy.astype(F), xlo, ylo)
+
+
+def local_laplacian(inp, levels, alpha, beta, out_shape=None, in_mins=(0, 0, 0), out_mins=(0, 0, 0), J=8):
+    """inp: uint16 [c, h, w] whose element [0, 0, 0] sits at coordinates in_mins = (x, y, c); alpha as the filter
+    receives it (already divided by levels - 1).  Returns uint16 [C, H, W] at out_mins."""
+    alpha, beta = F(alpha), F(beta)
+    ic, ih, iw = inp.shape
+    if out_shape is None:
+        out_shape = inp.shape
+    C, H, W = out_shape
+    ix0, iy0, ic0 = in_mins
+    ox0, oy0, oc0 = out_mins
+    # --- bounds: O_j = box of outGPyramid[j] / lPyramid[j]; G_j = box of gPyramid[j] / inGPyramid[j] -------------------
+    O = [(ox0, ox0 + W - 1, oy0, oy0 + H - 1)]
+    for j in range(1, J):
+        xl, xh, yl, yh = O[j - 1]
+        O.append(((xl - 1) >> 1, (xh + 1) >> 1, (yl - 1) >> 1, (yh + 1) >> 1))
+    G = [None] * J
+    G[J - 1] = O[J - 1]
+    for j in range(J - 2, -1, -1):
+        xl, xh, yl, yh = G[j + 1]
+        d = (2 * xl - 1, 2 * xh + 2, 2 * yl - 1, 2 * yh + 2)
+        G[j] = (min(O[j][0], d[0]), max(O[j][1], d[1]), min(O[j][2], d[2]), max(O[j][3], d[3]))
+    # --- remap LUT on every index it can be asked for ----------------------------------------------------------------
+    lm1 = levels - 1
+    lut_x = np.arange(-256 * lm1, 256 * lm1 + 1)
+    fx = lut_x.astype(F) * F(1.0 / 256.0)
+    lut = (alpha * fx) * halide_exp((-fx * fx) * F(0.5))
+    # --- gray on G_0 from the edge-clamped input -----------------------------------------------------------------------
+    gx = np.arange(G[0][0], G[0][1] + 1)
+    gy = np.arange(G[0][2], G[0][3] + 1)
+    cx = np.clip(gx, ix0, ix0 + iw - 1) - ix0
+    cy = np.clip(gy, iy0, iy0 + ih - 1) - iy0
+    inv65535 = F(1.0 / 65535.0)
+
+    def floating(c):
+        cc = min(max(c, ic0), ic0 + ic - 1) - ic0
+        return inp[cc][cy[:, None], cx[None, :]].astype(F) * inv65535
+
+    gray = F(0.299) * floating(0) + F(0.587) * floating(1) + F(0.114) * floating(2)
+    # --- gPyramid[0] on G_0 ------------------------------------------------------------------------------------------------
+    flm1 = F(lm1)
+    inv_lm1 = F(1.0) / flm1
+    idx = np.clip(((gray * flm1) * F(256.0)).astype(np.int32), 0, lm1 * 256)
+    ks = np.arange(levels)
+    level = ks.astype(F) * inv_lm1
+    g0 = beta * (gray[:, :, None] - level[None, None, :]) + level[None, None, :]
+    g0 = g0 + lut[(idx[:, :, None] - 256 * ks[None, None, :]) + 256 * lm1]
+    gP = [Field(g0.astype(F), G[0][0], G[0][2])]
+    inG = [Field(gray.astype(F), G[0][0], G[0][2])]
+    for j in range(1, J):
+        gP.append(_down(gP[j - 1], *G[j]))
+        inG.append(_down(inG[j - 1], *G[j]))
+    # --- Laplacian pyramid of the processed stack, output pyramids ---------------------------------------------------------
+    outG = [None] * J
+    for j in range(J - 1, -1, -1):
+        xl, xh, yl, yh = O[j]
+        xs, ys = np.arange(xl, xh + 1), np.arange(yl, yh + 1)
+        lP = gP[j].at(xs, ys) if j == J - 1 else gP[j].at(xs, ys) - _up(gP[j + 1], xl, xh, yl, yh).arr
+        lev = inG[j].at(xs, ys) * flm1
+        li = np.clip(lev.astype(np.int32), 0, levels - 2)
+        lf = lev - li.astype(F)
+        yy, xx = np.meshgrid(np.arange(len(ys)), np.arange(len(xs)), indexing="ij")
+        outL = (F(1.0) - lf) * lP[yy, xx, li] + lf * lP[yy, xx, li + 1]
+        if j == J - 1:
+            outG[j] = Field(outL.astype(F), xl, yl)
+        else:
+            outG[j] = Field((_up(outG[j + 1], xl, xh, yl, yh).arr + outL).astype(F), xl, yl)
+    # --- colour ---------------------------------------------------------------------------------------------------------------
+    eps = F(0.01)
+    xs, ys = np.arange(ox0, ox0 + W), np.arange(oy0, oy0 + H)
+    g_out = inG[0].at(xs, ys)
+    num = outG[0].arr + eps
+    den = g_out + eps
+    out = np.empty((C, H, W), np.uint16)
+    for c in range(C):
+        ch = inp[oc0 + c - ic0][(ys - iy0)[:, None], (xs - ix0)[None, :]].astype(F)  # unclamped read: must be inside the input
+        color = (ch * num) / den
+        out[c] = np.maximum(np.minimum(color, F(65535.0)), F(0.0)).astype(np.uint16)
+    return out
+
+
+def stencil_chain(inp, out_shape=None, in_mins=(0, 0), out_mins=(0, 0), stencils=32):
+    """inp: uint16 [h, w] at in_mins = (x, y).  32 chained 5x5 stencils, weight (i+3)(j+3), all in uint16 (wraps);
+    only the input is edge-clamped, every stage is evaluated on the region the next one reads."""
+    ih, iw = inp.shape
+    if out_shape is None:
+        out_shape = inp.shape
+    H, W = out_shape
+    ix0, iy0 = in_mins
+    ox0, oy0 = out_mins
+    r = 2 * stencils
+    xs = np.arange(ox0 - r, ox0 + W + r)
+    ys = np.arange(oy0 - r, oy0 + H + r)
+    cur = inp[(np.clip(ys, iy0, iy0 + ih - 1) - iy0)[:, None], (np.clip(xs, ix0, ix0 + iw - 1) - ix0)[None, :]].astype(np.uint16)
+    for _ in range(stencils):
+        h, w = cur.shape
+        acc = np.zeros((h - 4, w - 4), np.uint16)
+        for i in range(-2, 3):        # x offset, outer
+            for j in range(-2, 3):    # y offset, inner
+                acc = acc + np.uint16((i + 3) * (j + 3)) * cur[2 + j:h - 2 + j, 2 + i:w - 2 + i]
+        cur = acc
+    return cur
