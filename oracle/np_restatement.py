@@ -184,3 +184,130 @@ def stencil_chain(inp, out_shape=None, in_mins=(0, 0), out_mins=(0, 0), stencils
                 acc = acc + np.uint16((i + 3) * (j + 3)) * cur[2 + j:h - 2 + j, 2 + i:w - 2 + i]
         cur = acc
     return cur
+
+
+def _clamped2(inp, mins, xs, ys):
+    """repeat_edge(input)(xs, ys) for a 2-D array at mins = (x, y): outer product of row / column index vectors."""
+    h, w = inp.shape
+    return inp[(np.clip(ys, mins[1], mins[1] + h - 1) - mins[1])[:, None], (np.clip(xs, mins[0], mins[0] + w - 1) - mins[0])[None, :]]
+
+
+def bilateral_grid(inp, r_sigma, out_shape=None, in_mins=(0, 0), out_mins=(0, 0), s_sigma=8):
+    """apps/bilateral_grid/bilateral_grid_generator.cpp:17-67.  inp: float32 [h, w] at in_mins = (x, y)."""
+    inp = inp.astype(F)
+    if out_shape is None:
+        out_shape = inp.shape
+    H, W = out_shape
+    ox0, oy0 = out_mins
+    s = s_sigma
+    inv_r = F(1.0) / F(r_sigma)
+    xs, ys = np.arange(ox0, ox0 + W), np.arange(oy0, oy0 + H)
+    # cells read by the slice: xi .. xi+1, yi .. yi+1; the blurs widen that by 2 cells per axis
+    cx_lo, cx_hi = (ox0 // s) - 2, ((ox0 + W - 1) // s) + 1 + 2
+    cy_lo, cy_hi = (oy0 // s) - 2, ((oy0 + H - 1) // s) + 1 + 2
+    z_lo, z_hi = -4, int(np.floor(float(inv_r))) + 6  # generous: bins that are never hit stay 0
+    ncx, ncy, nz = cx_hi - cx_lo + 1, cy_hi - cy_lo + 1, z_hi - z_lo + 1
+    hist = np.zeros((ncy, ncx, nz, 2), F)
+    cys, cxs = np.arange(cy_lo, cy_hi + 1), np.arange(cx_lo, cx_hi + 1)
+    yy, xx = np.meshgrid(np.arange(ncy), np.arange(ncx), indexing="ij")
+    for ry in range(s):          # RDom r(0, s, 0, s): r.x is the inner loop
+        for rx in range(s):
+            val = _clamped2(inp, in_mins, cxs * s + rx - s // 2, cys * s + ry - s // 2)
+            val = np.maximum(np.minimum(val, F(1.0)), F(0.0))
+            zi = (val * inv_r + F(0.5)).astype(np.int32)
+            hist[yy, xx, zi - z_lo, 0] += val
+            hist[yy, xx, zi - z_lo, 1] += F(1.0)
+
+    def blur5(a, axis):
+        n = a.shape[axis]
+
+        def sl(o):
+            idx = [slice(None)] * a.ndim
+            idx[axis] = slice(2 + o, n - 2 + o)
+            return a[tuple(idx)]
+        return (((sl(-2) + sl(-1) * F(4)) + sl(0) * F(6)) + sl(1) * F(4)) + sl(2)
+
+    blurz = blur5(hist, 2)        # z range shrinks by 2 at each end
+    blurx = blur5(blurz, 1)
+    blury = blur5(blurx, 0)       # now cells [cx_lo+2, cx_hi-2] x [cy_lo+2, cy_hi-2], z [z_lo+2, z_hi-2]
+    bx0, by0, bz0 = cx_lo + 2, cy_lo + 2, z_lo + 2
+    val = inp[(ys - in_mins[1])[:, None], (xs - in_mins[0])[None, :]]  # unclamped read: must lie inside the input
+    val = np.maximum(np.minimum(val, F(1.0)), F(0.0))
+    zv = val * inv_r
+    zi = zv.astype(np.int32)
+    zf = zv - zi.astype(F)
+    xf = ((xs % s).astype(F) * F(1.0 / s))[None, :]
+    yf = ((ys % s).astype(F) * F(1.0 / s))[:, None]
+    xi = (xs // s - bx0)[None, :] + np.zeros((H, 1), np.int64)
+    yi = (ys // s - by0)[:, None] + np.zeros((1, W), np.int64)
+
+    def g(dx, dy, dz, c):
+        return blury[yi + dy, xi + dx, zi - bz0 + dz, c]
+
+    def interp(c):
+        return _lerp(_lerp(_lerp(g(0, 0, 0, c), g(1, 0, 0, c), xf), _lerp(g(0, 1, 0, c), g(1, 1, 0, c), xf), yf),
+                     _lerp(_lerp(g(0, 0, 1, c), g(1, 0, 1, c), xf), _lerp(g(0, 1, 1, c), g(1, 1, 1, c), xf), yf), zf)
+
+    return (interp(0) / interp(1)).astype(F)
+
+
+def fast_exp(x_full):
+    """src/IROperator.cpp:1616-1643."""
+    x_full = x_full.astype(F)
+    ln2 = np.log(F(2.0), dtype=F)                 # logf(2.0)
+    scaled = x_full * F(1.0 / float(ln2))         # x / const -> x * fold(1 / const), folded in double
+    k_real = np.floor(scaled)
+    k = k_real.astype(np.int32)
+    x = x_full - k_real * ln2
+    c = [F(v) for v in (0.01314350012789660196, 0.03668965196652099192, 0.16873890085469545053, 0.49970514590562437052, 1.0, 1.0)]
+    x2 = x * x
+    even, odd = c[0], c[1]
+    for i in range(2, 6):
+        if i & 1:
+            odd = odd * x2 + c[i]
+        else:
+            even = even * x2 + c[i]
+    result = even * x + odd
+    biased = np.clip(k + 127, 0, 255)
+    return (result * (biased.astype(np.uint32) << np.uint32(23)).view(F)).astype(F)
+
+
+def nl_means(inp, patch_size, search_area, sigma, out_shape=None, in_mins=(0, 0, 0), out_mins=(0, 0, 0)):
+    """apps/nl_means/nl_means_generator.cpp:17-63.  inp: float32 [c, h, w] at in_mins = (x, y, c); output has 3 channels."""
+    inp = inp.astype(F)
+    ic, ih, iw = inp.shape
+    if out_shape is None:
+        out_shape = (3, ih, iw)
+    _, H, W = out_shape
+    ix0, iy0, ic0 = in_mins
+    ox0, oy0, _ = out_mins
+    sg, p, sa = F(sigma), patch_size, search_area
+    inv_sigma_sq = F(-1.0) / (((sg * sg) * F(p)) * F(p))
+    hp = p // 2
+
+    def clamped(c, xs, ys):
+        cc = min(max(c, ic0), ic0 + ic - 1) - ic0
+        return _clamped2(inp[cc], (ix0, iy0), xs, ys)
+
+    xs, ys = np.arange(ox0, ox0 + W), np.arange(oy0, oy0 + H)
+    xs_w = np.arange(ox0 - hp, ox0 + W - hp + p - 1 + 1)     # x range blur_d reads of blur_d_y
+    ys_w = np.arange(oy0 - hp, oy0 + H - hp + p - 1 + 1)     # y range blur_d_y reads of d
+    acc = np.zeros((4, H, W), F)
+    for sy in range(-(sa // 2), -(sa // 2) + sa):             # s_dom.y outer, s_dom.x inner
+        for sx in range(-(sa // 2), -(sa // 2) + sa):
+            d = np.zeros((len(ys_w), len(xs_w)), F)
+            for c in range(3):
+                t = clamped(c, xs_w, ys_w) - clamped(c, xs_w + sx, ys_w + sy)
+                d = d + t * t
+            blur_d_y = np.zeros((H, len(xs_w)), F)
+            for r in range(p):
+                blur_d_y = blur_d_y + d[r:r + H, :]
+            blur_d = np.zeros((H, W), F)
+            for r in range(p):
+                blur_d = blur_d + blur_d_y[:, r:r + W]
+            w = fast_exp(blur_d * inv_sigma_sq)
+            for c in range(3):
+                acc[c] = acc[c] + w * clamped(c, xs + sx, ys + sy)
+            acc[3] = acc[3] + w * F(1.0)
+    out = acc[:3] / acc[3][None]
+    return np.maximum(np.minimum(out, F(1.0)), F(0.0)).astype(F)

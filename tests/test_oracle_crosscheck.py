@@ -44,3 +44,26 @@ def test_stencil_chain_restatements_agree(oracle):
     assert np.array_equal(oracle.stencil_chain(img), npr.stencil_chain(img))
     kw = dict(out_shape=(30, 40), in_mins=(3, -2), out_mins=(-10, -9))
     assert np.array_equal(oracle.stencil_chain(img, **kw), npr.stencil_chain(img, **kw))
+
+
+def test_bilateral_grid_restatements_agree(oracle):
+    from oracle import np_restatement as npr
+    from util import f32_frame
+    img = f32_frame((53, 77), 3)
+    a, b = oracle.bilateral_grid(img, 0.1), npr.bilateral_grid(img, 0.1)
+    assert np.array_equal(a, b), float(np.abs(a - b).max())
+    kw = dict(out_shape=(30, 41), in_mins=(-13, 5), out_mins=(3, 12))
+    a, b = oracle.bilateral_grid(img, 0.25, **kw), npr.bilateral_grid(img, 0.25, **kw)
+    assert np.array_equal(a, b), float(np.abs(a - b).max())
+
+
+def test_nl_means_restatements_agree(oracle):
+    from oracle import np_restatement as npr
+    from util import f32_frame
+    img = f32_frame((3, 31, 45), 5)
+    for patch, search in ((3, 7), (7, 7), (5, 3)):
+        a, b = oracle.nl_means(img, patch, search, 0.12), npr.nl_means(img, patch, search, 0.12)
+        assert np.array_equal(a, b), (patch, search, float(np.abs(a - b).max()))
+    kw = dict(out_shape=(3, 20, 31), in_mins=(-4, 2, 0), out_mins=(1, 6, 0))
+    a, b = oracle.nl_means(img, 3, 7, 0.2, **kw), npr.nl_means(img, 3, 7, 0.2, **kw)
+    assert np.array_equal(a, b), float(np.abs(a - b).max())
