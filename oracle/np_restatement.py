@@ -1,4 +1,4 @@
-"""Second, independently structured restatement of two pipelines in numpy — TEST INFRASTRUCTURE ONLY.
+"""Second, independently structured restatement of the pipelines in numpy — TEST INFRASTRUCTURE ONLY.
 
 oracle/*.cpp evaluates the generators pixel by pixel through memoised recursive lambdas; this file evaluates the same
 Func definitions as whole-array float32 numpy expressions over explicitly inferred index ranges (the way Halide's
@@ -8,7 +8,7 @@ oracle much less likely.  tests/test_oracle_crosscheck.py compares them.
 
 Follows: apps/local_laplacian/local_laplacian_generator.cpp:19-87 (algorithm), :262-282 (downsample / upsample);
 src/IROperator.cpp:921-966 + :33-62 (halide_exp, evaluate_polynomial); src/Lerp.cpp:126-128 (lerp);
-apps/stencil_chain/stencil_chain_generator.cpp:17-30.  Halide semantics used: Euclidean integer / and %, float
+apps/stencil_chain/stencil_chain_generator.cpp:17-30; the other generators are cited at their functions.  Halide semantics used: Euclidean integer / and %, float
 x / const -> x * fold(1/const), no FMA contraction, lerp(z, o, w) = z*(1-w) + o*w, clamp = max(min(a, hi), lo).
 """
 import numpy as np
@@ -311,3 +311,187 @@ def nl_means(inp, patch_size, search_area, sigma, out_shape=None, in_mins=(0, 0,
             acc[3] = acc[3] + w * F(1.0)
     out = acc[:3] / acc[3][None]
     return np.maximum(np.minimum(out, F(1.0)), F(0.0)).astype(F)
+
+
+# ---- camera_pipe (apps/camera_pipe/camera_pipe_generator.cpp:16-35, 37-152, 240-425) -------------------------------------
+# Every Func is a Python function of integer index grids (X, Y broadcast to one shape), evaluated by plain recursion
+# with no memoisation — slow, but there is no region bookkeeping to get wrong; small frames only.
+
+def halide_log(x_full):
+    """src/IROperator.cpp:845-919."""
+    x_full = np.asarray(x_full, F)
+    use_nan, use_neg_inf = x_full < 0, x_full == 0
+    patched = np.where(use_nan | use_neg_inf, F(1.0), x_full).astype(F)
+    iv = patched.view(np.int32)
+    no_exp = iv & np.int32(-2139095041)          # 0x807fffff
+    new_e = no_exp >> 22
+    new_biased = 127 - new_e
+    exponent = (iv >> 23) - new_biased
+    reduced = (no_exp | (new_biased << 23)).astype(np.int32).view(F)
+    c = [F(v) for v in (0.05111976432738144643, -0.11793923497136414580, 0.14971993724699017569, -0.16862004708254804686,
+                        0.19980668101718729313, -0.24991211576292837737, 0.33333435275479328386, -0.50000106292873236491,
+                        1.0, 0.0)]
+    x1 = reduced - F(1.0)
+    x2 = x1 * x1
+    even, odd = c[0], c[1]
+    for i in range(2, 10):
+        if i & 1:
+            odd = odd * x2 if c[i] == 0 else odd * x2 + c[i]
+        else:
+            even = even * x2 if c[i] == 0 else even * x2 + c[i]
+    result = even * x1 + odd
+    result = result + exponent.astype(F) * np.log(F(2.0), dtype=F)
+    return np.where(use_nan, F(np.nan), np.where(use_neg_inf, F(-np.inf), result)).astype(F)
+
+
+def halide_pow(x, y):
+    """pow_f32 lowering, src/CodeGen_LLVM.cpp:3925-3942 (only the branches x >= 0 can reach here)."""
+    x, y = np.asarray(x, F), np.asarray(y, F)
+    with np.errstate(all="ignore"):
+        p = halide_exp(halide_log(np.abs(x)) * y)
+    return np.where(x > 0, p, np.where(y == 0, F(1.0), F(0.0))).astype(F)
+
+
+def camera_pipe(raw, m3200, m7000, color_temp, gamma, contrast, sharpen_strength, black, white, out_shape, in_mins=(0, 0),
+                out_mins=(0, 0, 0)):
+    """raw: uint16 [h, w] at in_mins = (x, y); returns uint8 [3, H, W] at out_mins = (x, y, c)."""
+    u16, i16, i32, u32, u8 = np.uint16, np.int16, np.int32, np.uint32, np.uint8
+    C, H, W = out_shape
+
+    def inp(X, Y):  # unclamped: the caller supplies the region the pipeline reads
+        xi, yi = X - in_mins[0], Y - in_mins[1]
+        assert xi.min() >= 0 and yi.min() >= 0 and xi.max() < raw.shape[1] and yi.max() < raw.shape[0], "raw read out of bounds"
+        return raw[yi, xi]
+
+    def shifted(X, Y):
+        return inp(X + 16, Y + 12)
+
+    def denoised(X, Y):
+        a = np.maximum(np.maximum(shifted(X - 2, Y), shifted(X + 2, Y)), np.maximum(shifted(X, Y - 2), shifted(X, Y + 2)))
+        return np.maximum(np.minimum(shifted(X, Y), a), u16(0))
+
+    def deint(X, Y, c):
+        return denoised(2 * X + (c & 1), 2 * Y + (c >> 1))
+
+    def avg(a, b):  # (widen(a) + b + 1) / 2, narrowed back
+        wide = {u16: u32, u8: u16}[a.dtype.type]
+        return ((a.astype(wide) + b.astype(wide) + wide(1)) // wide(2)).astype(a.dtype)
+
+    def absd(a, b):
+        return np.where(a > b, a - b, b - a).astype(a.dtype)
+
+    g_gr = lambda X, Y: deint(X, Y, 0)
+    r_r = lambda X, Y: deint(X, Y, 1)
+    b_b = lambda X, Y: deint(X, Y, 2)
+    g_gb = lambda X, Y: deint(X, Y, 3)
+
+    def g_r(X, Y):
+        gv, gvd = avg(g_gb(X, Y - 1), g_gb(X, Y)), absd(g_gb(X, Y - 1), g_gb(X, Y))
+        gh, ghd = avg(g_gr(X + 1, Y), g_gr(X, Y)), absd(g_gr(X + 1, Y), g_gr(X, Y))
+        return np.where(ghd < gvd, gh, gv)
+
+    def g_b(X, Y):
+        gv, gvd = avg(g_gr(X, Y + 1), g_gr(X, Y)), absd(g_gr(X, Y + 1), g_gr(X, Y))
+        gh, ghd = avg(g_gb(X - 1, Y), g_gb(X, Y)), absd(g_gb(X - 1, Y), g_gb(X, Y))
+        return np.where(ghd < gvd, gh, gv)
+
+    # uint16 arithmetic wraps (numpy does the same for same-typed arrays)
+    def r_gr(X, Y):
+        return (g_gr(X, Y) - avg(g_r(X, Y), g_r(X - 1, Y))) + avg(r_r(X - 1, Y), r_r(X, Y))
+
+    def b_gr(X, Y):
+        return (g_gr(X, Y) - avg(g_b(X, Y), g_b(X, Y - 1))) + avg(b_b(X, Y), b_b(X, Y - 1))
+
+    def r_gb(X, Y):
+        return (g_gb(X, Y) - avg(g_r(X, Y), g_r(X, Y + 1))) + avg(r_r(X, Y), r_r(X, Y + 1))
+
+    def b_gb(X, Y):
+        return (g_gb(X, Y) - avg(g_b(X, Y), g_b(X + 1, Y))) + avg(b_b(X, Y), b_b(X + 1, Y))
+
+    def r_b(X, Y):
+        rp = (g_b(X, Y) - avg(g_r(X, Y), g_r(X - 1, Y + 1))) + avg(r_r(X, Y), r_r(X - 1, Y + 1))
+        rpd = absd(r_r(X, Y), r_r(X - 1, Y + 1))
+        rn = (g_b(X, Y) - avg(g_r(X - 1, Y), g_r(X, Y + 1))) + avg(r_r(X - 1, Y), r_r(X, Y + 1))
+        rnd = absd(r_r(X - 1, Y), r_r(X, Y + 1))
+        return np.where(rpd < rnd, rp, rn)
+
+    def b_r(X, Y):
+        bp = (g_r(X, Y) - avg(g_b(X, Y), g_b(X + 1, Y - 1))) + avg(b_b(X, Y), b_b(X + 1, Y - 1))
+        bpd = absd(b_b(X, Y), b_b(X + 1, Y - 1))
+        bn = (g_r(X, Y) - avg(g_b(X + 1, Y), g_b(X, Y - 1))) + avg(b_b(X + 1, Y), b_b(X, Y - 1))
+        bnd = absd(b_b(X + 1, Y), b_b(X, Y - 1))
+        return np.where(bpd < bnd, bp, bn)
+
+    def interleave(f00, f10, f01, f11):  # interleave_y(interleave_x(f00, f10), interleave_x(f01, f11)); Euclidean / and %
+        def out(X, Y):
+            hx, hy = X >> 1, Y >> 1
+            top = np.where((X & 1) == 0, f00(hx, hy), f10(hx, hy))
+            bot = np.where((X & 1) == 0, f01(hx, hy), f11(hx, hy))
+            return np.where((Y & 1) == 0, top, bot)
+        return out
+
+    demosaiced = [interleave(r_gr, r_r, r_b, r_gb), interleave(g_gr, g_r, g_b, g_gb), interleave(b_gr, b_r, b_b, b_gb)]
+
+    # colour matrix, Q8.8
+    kelvin = F(color_temp)
+    alpha = (F(1.0) / kelvin - F(1.0) / F(3200)) / (F(1.0) / F(7000) - F(1.0) / F(3200))
+    val = m3200.astype(F) * alpha + m7000.astype(F) * (F(1.0) - alpha)
+    matrix = (val * F(256.0)).astype(i16)        # [row y][col x]; matrix(x, y) in the generator
+
+    def corrected(X, Y, c):
+        ir, ig, ib = (demosaiced[k](X, Y).astype(u16).view(i16).astype(i32) for k in range(3))
+        m = matrix.astype(i32)
+        v = m[c, 3] + m[c, 0] * ir + m[c, 1] * ig + m[c, 2] * ib
+        return (v >> 8).astype(i16)              # Euclidean / 256, then wrap to int16
+
+    # tone curve LUT on [0, 1023]
+    xs = np.arange(1024, dtype=i32)
+    min_raw, max_raw = i32(black), i32(white)
+    inv_range = F(1.0) / F(max_raw - min_raw)
+    bq = F(2.0) - halide_pow(F(2.0), F(contrast) * F(0.01))
+    aq = F(2.0) - F(2.0) * bq
+    xf = np.maximum(np.minimum((xs - min_raw).astype(F) * inv_range, F(1.0)), F(0.0))
+    g = halide_pow(xf, F(1.0) / F(gamma))
+    omg = F(1.0) - g
+    z = np.where(g > F(0.5), F(1.0) - ((aq * omg) * omg + bq * omg), (aq * g) * g + bq * g).astype(F)
+    cval = np.maximum(np.minimum(z * F(255.0) + F(0.5), F(255.0)), F(0.0)).astype(u8)
+    curve = np.where(xs <= min_raw, u8(0), np.where(xs > max_raw, u8(255), cval)).astype(u8)
+
+    def curved(X, Y, c):
+        return curve[np.clip(corrected(X, Y, c), 0, 1023)]
+
+    sv = F(sharpen_strength) * F(32)
+    strength = u8(255) if sv >= F(255.0) else u8(max(sv, F(0.0)))      # u8_sat of a float
+
+    def blur121(a, b, c):
+        return avg(avg(a, c), b)
+
+    def unsharp_y(X, Y, c):
+        return blur121(curved(X, Y - 1, c), curved(X, Y, c), curved(X, Y + 1, c))
+
+    def unsharp(X, Y, c):
+        return blur121(unsharp_y(X - 1, Y, c), unsharp_y(X, Y, c), unsharp_y(X + 1, Y, c))
+
+    def sharpened(X, Y, c):
+        cur = curved(X, Y, c)
+        mask = cur.astype(i16) - unsharp(X, Y, c).astype(i16)
+        t = (mask * i16(strength)) >> 5          # int16 product wraps; Euclidean / 32
+        return np.clip(cur.astype(i16) + t, 0, 255).astype(u8)
+
+    Y, X = np.meshgrid(np.arange(out_mins[1], out_mins[1] + H), np.arange(out_mins[0], out_mins[0] + W), indexing="ij")
+    return np.stack([sharpened(X, Y, out_mins[2] + c) for c in range(C)])
+
+
+def conv_layer(inp, filt, bias):
+    """apps/conv_layer/conv_layer_generator.cpp:18-25: conv = bias; conv += filter(c, r.y, r.z, r.x) * input(r.x, x + r.y,
+    y + r.z, n) over RDom r(ci, kx, ky) with ci innermost, then relu.  Arrays are outermost-first: inp [N, H+2, W+2, CI],
+    filt [CI, ky, kx, CO] (Halide filter(c, kx, ky, ci)), bias [CO]."""
+    n, hp, wp, ci = inp.shape
+    co = bias.shape[0]
+    H, W = hp - 2, wp - 2
+    acc = np.broadcast_to(bias.astype(F), (n, H, W, co)).copy()
+    for ky in range(3):
+        for kx in range(3):
+            for c in range(ci):
+                acc = acc + filt[c, ky, kx, :].astype(F)[None, None, None, :] * inp[:, ky:ky + H, kx:kx + W, c].astype(F)[..., None]
+    return np.maximum(acc, F(0.0))

@@ -67,3 +67,29 @@ def test_nl_means_restatements_agree(oracle):
     kw = dict(out_shape=(3, 20, 31), in_mins=(-4, 2, 0), out_mins=(1, 6, 0))
     a, b = oracle.nl_means(img, 3, 7, 0.2, **kw), npr.nl_means(img, 3, 7, 0.2, **kw)
     assert np.array_equal(a, b), float(np.abs(a - b).max())
+
+
+def test_camera_pipe_restatements_agree(oracle):
+    from oracle import np_restatement as npr
+    rng = np.random.default_rng(12)
+    raw = rng.integers(0, 1024, (56 + 24, 72 + 32), dtype=np.uint16)
+    raw[rng.integers(0, raw.shape[0], 40), rng.integers(0, raw.shape[1], 40)] = 60000  # hot pixels
+    m32 = (rng.random((3, 4), dtype=np.float32) * 2 - 0.5).astype(np.float32)
+    m70 = (rng.random((3, 4), dtype=np.float32) * 2 - 0.5).astype(np.float32)
+    for args in ((3700.0, 2.0, 50.0, 1.0, 25, 1023), (5200.0, 1.8, 20.0, 2.5, 64, 900)):
+        a = oracle.camera_pipe(raw, m32, m70, *args, (3, 56, 72))
+        b = npr.camera_pipe(raw, m32, m70, *args, (3, 56, 72))
+        assert np.array_equal(a, b), (args, int((a != b).sum()))
+    a = oracle.camera_pipe(raw, m32, m70, 3700.0, 2.0, 50.0, 1.0, 25, 1023, (3, 30, 41), in_mins=(0, 0), out_mins=(3, 5, 0))
+    b = npr.camera_pipe(raw, m32, m70, 3700.0, 2.0, 50.0, 1.0, 25, 1023, (3, 30, 41), in_mins=(0, 0), out_mins=(3, 5, 0))
+    assert np.array_equal(a, b)
+
+
+def test_conv_layer_restatements_agree(oracle):
+    from oracle import np_restatement as npr
+    rng = np.random.default_rng(3)
+    inp = (rng.random((2, 8, 9, 16), dtype=np.float32) - 0.3).astype(np.float32)
+    filt = (rng.random((16, 3, 3, 24), dtype=np.float32) - 0.5).astype(np.float32)
+    bias = (rng.random(24, dtype=np.float32) - 0.5).astype(np.float32)
+    a, b = oracle.conv_layer(inp, filt, bias), npr.conv_layer(inp, filt, bias)
+    assert np.array_equal(a, b), float(np.abs(a - b).max())
