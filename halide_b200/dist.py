@@ -1,8 +1,13 @@
-"""Row-sharded multi-GPU execution: one process per GPU (torchrun), NCCL halo exchange inside the library.
+"""Row-sharded multi-GPU execution: one process per GPU (torchrun).
 
-torch.distributed is only the control plane here (broadcast of the NCCL unique id, barriers in
-bench.py); the data-path exchange — one ncclGroup of point-to-point halo messages per pyramid level
-— is issued by libhalide_b200.so on its compute stream (halide_b200/csrc/hb_dist.cu).
+local_laplacian: `RowSharder` joins the library's communicator and calls halide_b200_local_laplacian_sharded; the halo
+rows travel as NVLink stores into CUDA-IPC-mapped peer memory issued by the producing kernels themselves, one coarse
+pyramid level is gathered all-to-all and the coarser ones are replicated (halide_b200/csrc/local_laplacian.cu,
+hb_dist.cu).  torch.distributed is only the control plane there (broadcast of the NCCL unique id used
+for the bootstrap all-gather of the IPC handles and for the HALIDE_B200_HALO=nccl fallback, barriers in bench.py).
+
+The five filters that depend on other bands only through a halo of input rows are sharded by host logic at the end of
+this file (`InputHaloSharder`): a torch.distributed point-to-point row exchange, then the ordinary single-GPU filter.
 """
 import ctypes
 import os
