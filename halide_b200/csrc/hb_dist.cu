@@ -1,10 +1,15 @@
 // hb_dist.cu — one-process-per-GPU plumbing for the row-sharded pipelines.
 //
 // The reference has no distributed layer at all (SURVEY.md §2b "Collectives: none"); row-sharding with
-// halo exchange is new work.  Ranks are laid out top to bottom over the frame's rows;
-// the only data-path communication is a point-to-point halo exchange with the two row neighbours,
-// issued as one ncclGroup{send up, recv up, send down, recv down} on the compute stream so it orders
-// with the kernels without host synchronisation.
+// halo exchange is new work.  Ranks are laid out top to bottom over the frame's rows.
+// Two transports:
+//   * peer memory (default): producers store boundary rows straight into the neighbours' CUDA-IPC-mapped slabs and
+//     handshake through release/acquire flags (PeerIO in ll_kernels.cuh); this file holds the two helper kernels that
+//     are not fused into a pipeline kernel — peer_exchange_kernel (the caller-owned input rows) and peer_gather_kernel
+//     (all-to-all gather of one coarse pyramid level) — both bounded-spin so a protocol bug reports instead of hanging;
+//   * NCCL groups (HALIDE_B200_HALO=nccl): one ncclGroup{send up, recv up, send down, recv down} per level on the
+//     compute stream.
+// NCCL is also the bootstrap for the peer path (all-gather of the IPC handles and slab layouts).
 //
 // NCCL is bound at run time (dlopen "libnccl.so.2") so the library has no link-time dependency and
 // shares the NCCL instance torch already loaded when the host process is the Python bench/test.
