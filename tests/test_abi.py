@@ -168,3 +168,23 @@ def test_per_filter_bounds_queries(hb):
     q3 = B.bounds_query(np.float32, 3)
     assert F.nl_means(q3, 3, 7, 0.12, B.from_numpy(np.zeros((3, 20, 30), np.float32))) == 0
     assert [e for (_, e, _) in q3.shape()] == [30, 20, 3]
+
+
+def test_sharded_entry_point_requires_the_communicator(hb):
+    """halide_b200_local_laplacian_sharded validates like the plain filter and then refuses to run without
+    halide_b200_dist_init (host-only checks: no CUDA call before them)."""
+    import ctypes
+    import numpy as np
+    from halide_b200 import HalideBuffer as B
+    img = np.zeros((3, 64, 64), np.uint16)
+    bi, bo = B.from_numpy(img), B.from_numpy(np.zeros_like(img), host_dirty=False)
+    with pytest.raises(hb.HalideError) as e:
+        hb.lib.check(hb.capi.halide_b200_local_laplacian_sharded(bi.ptr, ctypes.c_int32(8), ctypes.c_float(1 / 7), ctypes.c_float(1.0),
+                                                                  bo.ptr, ctypes.c_int32(0), ctypes.c_int32(64)))
+    assert "halide_b200_dist_init" in str(e.value)
+    assert hb.capi.halide_b200_dist_rank() == 0 and hb.capi.halide_b200_dist_size() == 1
+    # type errors are reported before anything else, with the reference's code
+    bad = B.from_numpy(np.zeros((3, 64, 64), np.float32))
+    rc = hb.capi.halide_b200_local_laplacian_sharded(bad.ptr, ctypes.c_int32(8), ctypes.c_float(1 / 7), ctypes.c_float(1.0), bo.ptr,
+                                                    ctypes.c_int32(0), ctypes.c_int32(64))
+    assert rc == -3
