@@ -1,10 +1,10 @@
 """Row-sharded multi-GPU execution: one process per GPU (torchrun).
 
-local_laplacian: `RowSharder` joins the library's communicator and calls halide_b200_local_laplacian_sharded; the halo
-rows travel as NVLink stores into CUDA-IPC-mapped peer memory issued by the producing kernels themselves, one coarse
-pyramid level is gathered all-to-all and the coarser ones are replicated (halide_b200/csrc/local_laplacian.cu,
-hb_dist.cu).  torch.distributed is only the control plane there (broadcast of the NCCL unique id used
-for the bootstrap all-gather of the IPC handles and for the HALIDE_B200_HALO=nccl fallback, barriers in bench.py).
+local_laplacian: `RowSharder` joins the library's communicator and calls halide_b200_local_laplacian_sharded: one
+NCCL exchange of input halo rows with the row neighbours (every pyramid row a band needs beyond itself is recomputed
+from them), one all-to-all gather of a coarse pyramid level, the coarser levels replicated
+(halide_b200/csrc/local_laplacian.cu, ll_geom.h, hb_dist.cu).  torch.distributed is only the control
+plane there (broadcast of the NCCL unique id, barriers in bench.py).
 
 The five filters that depend on other bands only through a halo of input rows are sharded by host logic at the end of
 this file (`InputHaloSharder`): a torch.distributed point-to-point row exchange, then the ordinary single-GPU filter.
@@ -23,12 +23,22 @@ def band_rows(rank, world, frame_h):
     return lo, hi
 
 
-def band_geometry(frame_w, frame_h, lo, hi, first, last):
-    """Per-level rows owned / held by a band (host-only probe of ll_geom.h): list of 8 dicts."""
-    out = (ctypes.c_int32 * 64)()
-    check(lib.halide_b200_ll_band_geometry(frame_w, frame_h, lo, hi, int(first), int(last), out))
-    keys = ("own_lo", "own_hi", "stored_lo", "stored_hi", "own_o_lo", "own_o_hi", "stored_o_lo", "stored_o_hi")
-    return [dict(zip(keys, out[j * 8:(j + 1) * 8])) for j in range(8)]
+def band_geometry(frame_w, frame_h, lo, hi, first, last, jr):
+    """Per-level rows of a band with pyramid level `jr` gathered (host-only probe of ll_geom.h: ShardLevel): a list of
+    8 dicts {own, d, u, S} of inclusive (lo, hi) pairs — rows owned in the gather partition, Gaussian-side rows
+    computed and held, outGPyramid rows needed, the level's stored rows on the whole frame — and the input rows read."""
+    out = (ctypes.c_int32 * 66)()
+    check(lib.halide_b200_ll_band_geometry(frame_w, frame_h, lo, hi, int(first), int(last), int(jr), out))
+    levels = []
+    for j in range(8):
+        o = out[j * 8:(j + 1) * 8]
+        levels.append({"own": (o[0], o[1]), "d": (o[2], o[3]), "u": (o[4], o[5]), "S": (o[6], o[7])})
+    return levels, (out[64], out[65])
+
+
+def shard_plan_level(frame_w, frame_h, world):
+    """The pyramid level halide_b200_local_laplacian_sharded gathers all-to-all for this frame and rank count."""
+    return int(lib.halide_b200_ll_shard_plan_level(frame_w, frame_h, world))
 
 
 _initialised = False

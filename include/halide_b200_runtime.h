@@ -272,19 +272,22 @@ int halide_b200_dist_size(void);
 
 /* local_laplacian on this rank's row band of a frame whose rows are [frame_y_min, frame_y_min +
  * frame_y_extent): `input`/`output` hold the band's rows (all columns/channels) with dim[1].min in
- * frame coordinates.  One halo exchange with the row neighbours per pyramid level and sweep.
- * Bit-identical to the single-GPU filter on the whole frame. */
+ * frame coordinates; ranks are ordered top to bottom.  Communication per call: one exchange of input halo rows with
+ * the two row neighbours (every pyramid row a band needs beyond itself is recomputed from them) and one all-to-all
+ * gather of a coarse pyramid level.  Bit-identical to the single-GPU filter on the whole frame. */
 int halide_b200_local_laplacian_sharded(struct halide_buffer_t *input, int32_t levels, float alpha, float beta,
                                         struct halide_buffer_t *output, int32_t frame_y_min, int32_t frame_y_extent);
 
-/* Host-only probe of the band geometry (rows owned / held per pyramid level) for tests; out[64]. */
+/* Host-only probe of the band geometry for tests: with level jr gathered, out[j*8..j*8+7] = {own.lo, own.hi, d.lo, d.hi,
+ * u.lo, u.hi, S.lo, S.hi} per pyramid level j = 0..7 (rows owned in the gather partition / Gaussian-side rows computed and
+ * held / outGPyramid rows needed / the level's rows on the whole frame), out[64..65] = input rows read; out[66]. */
 int halide_b200_ll_band_geometry(int32_t frame_w, int32_t frame_h, int32_t band_lo, int32_t band_hi, int32_t first,
-                                 int32_t last, int32_t *out);
+                                 int32_t last, int32_t jr, int32_t *out);
 /* Row-sharded local_laplacian: pyramid level gathered all-to-all so that the coarser levels are computed
- * redundantly on every rank without further exchange.  0 = chosen by size (default), -1 = never (halos exchanged
- * level by level), n >= 2 = level n.  Collective setting: all ranks must agree. */
+ * redundantly on every rank without further exchange.  0 = chosen by size (default), n >= 2 = level n.
+ * Collective setting: all ranks must agree. */
 void halide_b200_ll_shard_coarse_level(int level);
-/* The level the sharded call would gather for a frame_w x frame_h frame over nranks ranks (8 = none); host-only. */
+/* The level the sharded call gathers for a frame_w x frame_h frame over nranks ranks; host-only. */
 int halide_b200_ll_shard_plan_level(int32_t frame_w, int32_t frame_h, int32_t nranks);
 /* Test hook: bitmask routing levels==8 calls through the generic kernels (1 down, 2 up, 4 final,
  * 8 no fused coarse launch, 16 general-layout final kernel) so both code paths stay covered by the parity tests. */

@@ -11,33 +11,49 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("frame_h,world", [(4320, 2), (2160 * 8, 8), (16384, 8), (2048, 2), (3000, 3)])
-def test_bands_tile_every_level(hb, frame_h, world):
+def test_shard_rows_cover_every_tap(hb, frame_h, world):
+    """Exchange-free row sharding (ll_geom.h: ShardLevel): the `own` rows partition every level, and the rows a rank
+    computes (d) cover every tap of the rows it needs one level up, so nothing but the input halo and the gathered level
+    ever crosses a shard boundary."""
     from halide_b200 import dist
     w = 3840
-    whole = dist.band_geometry(w, frame_h, 0, frame_h - 1, True, True)
-    per_rank = []
+    jr = dist.shard_plan_level(w, frame_h, world)
+    assert 2 <= jr <= 7
+    per_rank, needs = [], []
     for r in range(world):
         lo, hi = dist.band_rows(r, world, frame_h)
-        per_rank.append(dist.band_geometry(w, frame_h, lo, hi, r == 0, r == world - 1))
+        lv, need = dist.band_geometry(w, frame_h, lo, hi, r == 0, r == world - 1, jr)
+        per_rank.append(lv)
+        needs.append((lo, hi, need))
     for j in range(1, 8):
+        S = per_rank[0][j]["S"]
         # owned rows partition the whole frame's rows of that level, in rank order, without gaps
-        assert per_rank[0][j]["own_lo"] == whole[j]["own_lo"]
-        assert per_rank[-1][j]["own_hi"] == whole[j]["own_hi"]
+        assert per_rank[0][j]["own"][0] == S[0] and per_rank[-1][j]["own"][1] == S[1]
         for r in range(world - 1):
-            assert per_rank[r][j]["own_hi"] + 1 == per_rank[r + 1][j]["own_lo"], (j, r)
-            assert per_rank[r][j]["own_o_hi"] + 1 == per_rank[r + 1][j]["own_o_lo"], (j, r)
-            # halo: one row above, two below on the Gaussian side; one and one on the output side
-            assert per_rank[r][j]["stored_hi"] == per_rank[r][j]["own_hi"] + 2
-            assert per_rank[r + 1][j]["stored_lo"] == per_rank[r + 1][j]["own_lo"] - 1
-            assert per_rank[r][j]["stored_o_hi"] == per_rank[r][j]["own_o_hi"] + 1
-            assert per_rank[r + 1][j]["stored_o_lo"] == per_rank[r + 1][j]["own_o_lo"] - 1
-        # the taps of level j+1 (rows 2y-1 .. 2y+2) of every owned row stay inside the held rows of level j
-        if j < 7:
-            for r in range(world):
-                g, gn = per_rank[r][j], per_rank[r][j + 1]
-                lo_need = max(2 * gn["own_lo"] - 1, whole[j]["own_lo"])
-                hi_need = min(2 * gn["own_hi"] + 2, whole[j]["own_hi"])
-                assert g["stored_lo"] <= lo_need and hi_need <= g["stored_hi"], (j, r)
+            assert per_rank[r][j]["own"][1] + 1 == per_rank[r + 1][j]["own"][0], (j, r)
+    for r in range(world):
+        lo, hi, need = needs[r]
+        lv = per_rank[r]
+        assert lv[0]["u"] == (lo, hi)
+        for j in range(1, 8):
+            S, d, u = lv[j]["S"], lv[j]["d"], lv[j]["u"]
+            if j >= jr:
+                assert d == S   # replicated levels are held whole
+                continue
+            # outGPyramid[j] rows needed = the bilinear taps (y-1)//2, (y+1)//2 of the rows needed one level down
+            below = lv[j - 1]["u"]
+            assert u == ((below[0] - 1) // 2, (below[1] + 1) // 2)
+            # the rows computed cover the needed rows (inside the level) ...
+            assert d[0] <= max(u[0], S[0]) and min(u[1], S[1]) <= d[1]
+            # ... and the 1-3-3-1 taps 2y-1 .. 2y+2 of every row this rank computes one level up
+            nxt = lv[j + 1]["own"] if j + 1 == jr else lv[j + 1]["d"]
+            assert d[0] <= max(2 * nxt[0] - 1, S[0]) and min(2 * nxt[1] + 2, S[1]) <= d[1], (r, j)
+        # input rows read: the taps of level 1, clipped to the frame; the halo beyond the band is small and comes
+        # from the direct neighbours only
+        c1 = lv[1]["own"] if jr == 1 else lv[1]["d"]
+        assert need[0] <= max(2 * c1[0] - 1, 0) and min(2 * c1[1] + 2, frame_h - 1) <= need[1]
+        assert need[0] >= (0 if r == 0 else needs[r - 1][0]) and need[1] <= (frame_h - 1 if r == world - 1 else needs[r + 1][1])
+        assert lo - need[0] <= 2 ** (jr + 1) and need[1] - hi <= 2 ** (jr + 2)
 
 
 def test_band_rows_balanced():
@@ -58,9 +74,9 @@ def test_gloo_world2_control_plane(tmp_path):
         td.init_process_group("gloo")
         r, w = td.get_rank(), td.get_world_size()
         lo, hi = dist.band_rows(r, w, 4320)
-        geo = dist.band_geometry(3840, 4320, lo, hi, r == 0, r == w - 1)
+        geo, need = dist.band_geometry(3840, 4320, lo, hi, r == 0, r == w - 1, dist.shard_plan_level(3840, 4320, w))
         allg = [None] * w
-        td.all_gather_object(allg, (lo, hi, geo[1]["own_lo"], geo[1]["own_hi"]))
+        td.all_gather_object(allg, (lo, hi, geo[1]["own"][0], geo[1]["own"][1]))
         assert allg[0][1] + 1 == allg[1][0]
         assert allg[0][3] + 1 == allg[1][2]
         td.barrier()
@@ -77,18 +93,15 @@ def test_gloo_world2_control_plane(tmp_path):
 
 
 def test_coarse_level_choice(hb):
-    """The gathered level depends only on the frame and the rank count (every rank must pick the same one):
-    4K bands -> level 4 (1.2 MB per peer) at N=2, 4 and 8; smaller frames gather a finer level; more ranks
-    than flag slots, or the -1 override, fall back to level-by-level exchange (8 = no gather)."""
+    """The gathered level depends only on the frame and the rank count (every rank must pick the same one): the first
+    level whose per-rank rows are at most 1.25 MiB; the override forces a level."""
     lvl = hb.capi.halide_b200_ll_shard_plan_level
     assert lvl(3840, 2160 * 2, 2) == 4
     assert lvl(3840, 2160 * 4, 4) == 4
     assert lvl(3840, 2160 * 8, 8) == 4
+    assert lvl(16384, 16384, 8) == 5
+    assert lvl(16384, 16384, 2) == 6
     assert lvl(1000, 1280, 2) == 3
-    assert lvl(3840, 2160, 1) == 8
-    assert lvl(3840, 2160 * 16, 16) == 8
-    hb.capi.halide_b200_ll_shard_coarse_level(-1)
-    assert lvl(3840, 2160 * 2, 2) == 8
     hb.capi.halide_b200_ll_shard_coarse_level(5)
     assert lvl(3840, 2160 * 2, 2) == 5
     hb.capi.halide_b200_ll_shard_coarse_level(0)

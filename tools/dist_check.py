@@ -36,8 +36,8 @@ def main():
     b_in, b_out = HalideBuffer.from_numpy(band_in), HalideBuffer.from_numpy(band_out, host_dirty=False)
     want = full_out[:, sh.lo:sh.hi + 1, :]
     bad = 0
-    # coarse-level modes: level-by-level halo exchange (-1), gather level chosen by size (0), forced gather levels
-    modes = [int(m) for m in os.environ.get("DIST_CHECK_MODES", "-1,0,2,3,6").split(",")]
+    # gathered level: chosen by size (0), forced levels
+    modes = [int(m) for m in os.environ.get("DIST_CHECK_MODES", "0,2,3,6").split(",")]
     for mode in modes:
         halide_b200.capi.halide_b200_ll_shard_coarse_level(mode)
         for it in range(3):  # repeated: pooled scratch, epochs, ready/gather handshakes of consecutive calls
