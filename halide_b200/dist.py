@@ -143,8 +143,8 @@ def exchange_rows(band, own, need, rank, world, row_dim=-2):
     out = torch.empty(shape, dtype=band.dtype, device=band.device)
     covered = torch.zeros(shape[row_dim], dtype=torch.bool)
 
-    def wire(t):  # NCCL / gloo have no uint16: ship the bits
-        return t.view(torch.int16) if t.dtype == torch.uint16 else t
+    def wire(t):  # NCCL has no 16-bit integer types (and gloo no uint16): ship contiguous tensors as bytes
+        return t.view(torch.uint8) if t.dtype in (torch.uint16, torch.int16) else t
 
     lo, hi = max(need[0], own[0]), min(need[1], own[1])
     if lo <= hi:

@@ -20,7 +20,12 @@ def test_reference_arm_prints_one_contract_line():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
-    assert d["config"]["workload"] == "local_laplacian_4k" and d["data"] == "synthetic" and d["gpu_launches"] == 0
+    # the north-star configuration is the default workload; both arms print the same `config` object
+    assert d["config"]["workload"] == "local_laplacian_16k" and d["config"]["frame"] == [16384, 16384, 3]
+    assert d["scaling"] == "strong" and d["data"] == "synthetic" and d["gpu_launches"] == 0
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.make_config("local_laplacian_16k", 1)
 
 
 def test_product_arm_fails_loudly_without_cuda():
