@@ -194,21 +194,84 @@ void if_device_release(void *uc, const halide_device_interface_t *iface) {
     pool().release_unused();
 }
 
-int copy_span(halide_buffer_t *buf, bool to_host) {
-    if (any_empty(buf)) return 0;
-    int64_t lo, hi;
-    span_elems(buf, &lo, &hi);
-    size_t eb = hb::elem_bytes(buf);
-    size_t bytes = (size_t)(hi - lo + 1) * eb;
-    uint8_t *h = buf->host + lo * (int64_t)eb;
-    uint8_t *d = (uint8_t *)buf->device + lo * (int64_t)eb;
-    cudaError_t e = to_host ? cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, hb::stream())
-                            : cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, hb::stream());
-    if (e != cudaSuccess) {
-        return hb::fail(to_host ? halide_error_code_copy_to_host_failed : halide_error_code_copy_to_device_failed,
-                        "CUDA: memcpy of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+// Copy exactly the elements a buffer describes (reference: src/runtime/device_buffer_utils.h make_buffer_copy /
+// copy_memory_helper and cuda.cpp:884-1017): dimensions are sorted by stride, dimensions that are contiguous on both
+// sides are folded into one chunk, the next dimension becomes the rows of a 2-D memcpy and the remaining ones are
+// looped.  Gaps between rows / planes (padded or cropped buffers) are never touched on either side.
+struct CopyDim {
+    int64_t extent, sstride, dstride;  // strides in bytes
+};
+
+int copy_nd(uint8_t *dst, const uint8_t *src, CopyDim *dims, int n, size_t eb, cudaMemcpyKind kind, cudaStream_t s) {
+    for (int i = 0; i < n; i++) {
+        if (dims[i].extent <= 0) return 0;
+    }
+    // drop unit dimensions, sort by destination stride (insertion sort; n <= 4 in practice)
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        if (dims[i].extent != 1) dims[m++] = dims[i];
+    }
+    for (int i = 1; i < m; i++) {
+        CopyDim d = dims[i];
+        int j = i;
+        while (j > 0 && llabs(dims[j - 1].dstride) > llabs(d.dstride)) {
+            dims[j] = dims[j - 1];
+            j--;
+        }
+        dims[j] = d;
+    }
+    int64_t chunk = (int64_t)eb;
+    int first = 0;
+    while (first < m && dims[first].sstride == chunk && dims[first].dstride == chunk) {
+        chunk *= dims[first].extent;
+        first++;
+    }
+    auto fail_copy = [&](cudaError_t e) {
+        return hb::fail(kind == cudaMemcpyDeviceToHost ? halide_error_code_copy_to_host_failed
+                                                       : (kind == cudaMemcpyHostToDevice ? halide_error_code_copy_to_device_failed
+                                                                                         : halide_error_code_device_buffer_copy_failed),
+                        "CUDA: memcpy of %lld-byte chunks failed: %s", (long long)chunk, cudaGetErrorString(e));
+    };
+    if (first == m) {
+        cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)chunk, kind, s);
+        return e == cudaSuccess ? 0 : fail_copy(e);
+    }
+    // rows of a 2-D copy when both pitches are positive and at least one chunk wide; otherwise chunk by chunk
+    const CopyDim row = dims[first];
+    const bool two_d = row.sstride >= chunk && row.dstride >= chunk;
+    const int outer0 = two_d ? first + 1 : first;
+    int64_t idx[8] = {0};
+    for (;;) {
+        int64_t so = 0, dof = 0;
+        for (int i = outer0; i < m; i++) {
+            so += idx[i] * dims[i].sstride;
+            dof += idx[i] * dims[i].dstride;
+        }
+        cudaError_t e = two_d ? cudaMemcpy2DAsync(dst + dof, (size_t)row.dstride, src + so, (size_t)row.sstride, (size_t)chunk,
+                                                  (size_t)row.extent, kind, s)
+                              : cudaMemcpyAsync(dst + dof, src + so, (size_t)chunk, kind, s);
+        if (e != cudaSuccess) return fail_copy(e);
+        int i = outer0;
+        for (; i < m; i++) {
+            if (++idx[i] < dims[i].extent) break;
+            idx[i] = 0;
+        }
+        if (i == m) break;
     }
     return 0;
+}
+
+int copy_span(halide_buffer_t *buf, bool to_host) {
+    if (any_empty(buf)) return 0;
+    if (buf->dimensions > 8) return hb::fail(halide_error_code_bad_dimensions, "copy: buffers of more than 8 dimensions are not supported");
+    const size_t eb = hb::elem_bytes(buf);
+    CopyDim dims[8];
+    for (int d = 0; d < buf->dimensions; d++) {
+        dims[d] = {buf->dim[d].extent, (int64_t)buf->dim[d].stride * (int64_t)eb, (int64_t)buf->dim[d].stride * (int64_t)eb};
+    }
+    uint8_t *h = buf->host, *d = (uint8_t *)buf->device;
+    return to_host ? copy_nd(h, d, dims, buf->dimensions, eb, cudaMemcpyDeviceToHost, hb::stream())
+                   : copy_nd(d, h, dims, buf->dimensions, eb, cudaMemcpyHostToDevice, hb::stream());
 }
 
 int if_copy_to_host(void *uc, halide_buffer_t *buf) {
@@ -279,8 +342,56 @@ int if_device_and_host_free(void *uc, halide_buffer_t *buf) {
     return if_device_free(uc, buf);
 }
 
+// halide_buffer_copy (src/runtime/device_interface.cpp:154-205, cuda.cpp:884-1017): copy the region `dst` describes out of
+// `src` (which must cover it) — from the device side of src when that is the valid copy, to the device side of dst when
+// dst_iface is this interface, to its host side when dst_iface is null.  Dirty bits follow the reference's rules.
 int if_buffer_copy(void *uc, halide_buffer_t *src, const halide_device_interface_t *dst_iface, halide_buffer_t *dst) {
-    return hb::fail(halide_error_code_device_buffer_copy_failed, "buffer_copy is not provided by this runtime");
+    if (!src || !dst) return hb::fail(halide_error_code_buffer_is_null, "buffer_copy: buffer is null");
+    if (dst_iface && dst_iface != &g_cuda_interface) {
+        return hb::fail(halide_error_code_incompatible_device_interface, "buffer_copy: destination interface is not this runtime's");
+    }
+    if (src->dimensions != dst->dimensions || src->type.bits != dst->type.bits || src->dimensions > 8) {
+        return hb::fail(halide_error_code_device_buffer_copy_failed, "buffer_copy: source and destination differ in dimensions or element size");
+    }
+    const bool from_host = src->device == 0 || (src->flags & halide_buffer_flag_host_dirty) ||
+                           (src->host != nullptr && !(src->flags & halide_buffer_flag_device_dirty));
+    const bool to_host = dst_iface == nullptr;
+    if (from_host && !src->host) return hb::fail(halide_error_code_host_is_null, "buffer_copy: source has no valid copy");
+    if (to_host && !dst->host) return hb::fail(halide_error_code_host_is_null, "buffer_copy: destination host pointer is null");
+    if (!to_host) {
+        int r = if_device_malloc(uc, dst, dst_iface);
+        if (r) return r;
+    }
+    const size_t eb = hb::elem_bytes(src);
+    CopyDim dims[8];
+    int64_t src_off = 0;
+    for (int d = 0; d < src->dimensions; d++) {
+        const int lo = dst->dim[d].min, ext = dst->dim[d].extent;
+        if (ext > 0 && (lo < src->dim[d].min || lo + ext > src->dim[d].min + src->dim[d].extent)) {
+            return hb::fail(halide_error_code_access_out_of_bounds, "buffer_copy: destination region [%d, %d] of dimension %d is outside the source [%d, %d]",
+                            lo, lo + ext - 1, d, src->dim[d].min, src->dim[d].min + src->dim[d].extent - 1);
+        }
+        src_off += (int64_t)(lo - src->dim[d].min) * src->dim[d].stride * (int64_t)eb;
+        dims[d] = {ext, (int64_t)src->dim[d].stride * (int64_t)eb, (int64_t)dst->dim[d].stride * (int64_t)eb};
+    }
+    const uint8_t *sp = (from_host ? src->host : (const uint8_t *)src->device) + src_off;
+    uint8_t *dp = to_host ? dst->host : (uint8_t *)dst->device;
+    const cudaMemcpyKind kind = from_host ? (to_host ? cudaMemcpyHostToHost : cudaMemcpyHostToDevice)
+                                          : (to_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+    int r = copy_nd(dp, sp, dims, src->dimensions, eb, kind, hb::stream());
+    if (r) return r;
+    if (to_host || from_host) {  // host memory involved: the caller may touch it as soon as we return
+        cudaError_t e = cudaStreamSynchronize(hb::stream());
+        if (e != cudaSuccess) return hb::fail(halide_error_code_device_buffer_copy_failed, "CUDA: buffer_copy failed: %s", cudaGetErrorString(e));
+    }
+    if (to_host) {
+        dst->flags |= halide_buffer_flag_host_dirty;
+        dst->flags &= ~(uint64_t)halide_buffer_flag_device_dirty;
+    } else {
+        dst->flags |= halide_buffer_flag_device_dirty;
+        dst->flags &= ~(uint64_t)halide_buffer_flag_host_dirty;
+    }
+    return 0;
 }
 int if_device_crop(void *uc, const halide_buffer_t *src, halide_buffer_t *dst) {
     // Same allocation, shifted handle: dst->dim already holds the cropped mins.
@@ -602,6 +713,10 @@ int halide_copy_to_host(void *uc, halide_buffer_t *buf) {
 int halide_copy_to_device(void *uc, halide_buffer_t *buf, const halide_device_interface_t *iface) {
     if (!iface) iface = &g_cuda_interface;
     return iface->copy_to_device(uc, buf, iface);
+}
+// src/runtime/device_interface.cpp:154-205: a null dst_device_interface means "to the host side of dst".
+int halide_buffer_copy(void *uc, halide_buffer_t *src, const halide_device_interface_t *dst_iface, halide_buffer_t *dst) {
+    return if_buffer_copy(uc, src, dst_iface, dst);
 }
 void halide_device_release(void *uc, const halide_device_interface_t *iface) {
     if_device_release(uc, iface);

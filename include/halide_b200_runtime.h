@@ -221,6 +221,10 @@ int halide_device_malloc(void *user_context, struct halide_buffer_t *buf,
 int halide_device_free(void *user_context, struct halide_buffer_t *buf);
 int halide_device_sync(void *user_context, struct halide_buffer_t *buf);
 int halide_copy_to_host(void *user_context, struct halide_buffer_t *buf);
+/* Copy the region `dst` describes out of `src` (HalideRuntime.h halide_buffer_copy; src/runtime/device_interface.cpp:154-205):
+ * to dst's device side when dst_device_interface is halide_cuda_device_interface(), to its host side when it is NULL. */
+int halide_buffer_copy(void *user_context, struct halide_buffer_t *src,
+                       const struct halide_device_interface_t *dst_device_interface, struct halide_buffer_t *dst);
 int halide_copy_to_device(void *user_context, struct halide_buffer_t *buf,
                           const struct halide_device_interface_t *device_interface);
 void halide_device_release(void *user_context, const struct halide_device_interface_t *device_interface);

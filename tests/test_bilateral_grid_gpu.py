@@ -52,3 +52,18 @@ def test_constant_frame_is_fixed_point(hb):
     inp = np.full((4320, 7680), 0.37, np.float32)
     got = run(hb, inp, 0.1)
     assert np.allclose(got, 0.37, rtol=1e-5)
+
+
+def test_8k_random_frame_regions(hb, oracle):
+    """Config 3 size (7680 x 4320) on a RANDOM frame: regions of the full-size result against the oracle run on the crop
+    that determines them (grid cells are 8 px, the blurs reach 2 cells, the slice 1: a 64 px margin is ample; crops keep
+    their frame coordinates as mins because cell boundaries are absolute)."""
+    h, w = 4320, 7680
+    inp = f32_frame((h, w), 21)
+    got = run(hb, inp, 0.1)
+    for (y0, x0) in [(0, 0), (h - 96, w - 96), (2000, 3333), (4096 - 48, 4096 - 48)]:
+        n, m = 96, 64
+        ya, yb, xa, xb = max(0, y0 - m), min(h, y0 + n + m), max(0, x0 - m), min(w, x0 + n + m)
+        crop = np.ascontiguousarray(inp[ya:yb, xa:xb])
+        want = oracle.bilateral_grid(crop, 0.1, in_mins=(xa, ya), out_mins=(xa, ya))
+        close(got[y0:y0 + n, x0:x0 + n], want[y0 - ya:y0 - ya + n, x0 - xa:x0 - xa + n])

@@ -30,10 +30,7 @@ def test_input_halo_filters_sharded_match_single_gpu():
     """blur / nl_means / stencil_chain / bilateral_grid / camera_pipe row-sharded over 2 GPUs (NCCL row exchange +
     the ordinary filter on the extended band) equal the whole-frame call on one GPU (bit for bit for the integer
     pipelines, 1e-4 relative for the float ones)."""
-    if os.environ.get("HALIDE_B200_TEST_UNVALIDATED") != "1":
-        # written after round 1's GPU budget was spent: the host logic is covered on CPU (tests/test_dist_cpu.py), the
-        # NCCL run is not yet.  Run it once with HALIDE_B200_TEST_UNVALIDATED=1 on a 2-GPU box, then drop this gate.
-        pytest.skip("first hardware run pending (set HALIDE_B200_TEST_UNVALIDATED=1)")
+    # (first hardware run: profiles/r02_dist_rows_check_n2.log)
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",

@@ -88,9 +88,48 @@ def test_4k_tile_consistency(hb, oracle):
     assert np.array_equal(got[:, h - 160:, w - 160:], br[:, m - 160:, m - 160:])
 
 
+def _region_vs_oracle(oracle, img, got, y0, x0, n=128, margin=896):
+    """`got` = the filter's result on the whole frame `img`; compare its n x n region at (y0, x0) with the oracle run on
+    the crop that determines it (the footprint of 8 pyramid levels stays well inside `margin` px; pyramid coordinates
+    are absolute — the parity of x, y matters in down/upsample — so the crop keeps its frame coordinates as mins; where
+    the crop touches a frame edge it ends exactly there, so repeat_edge acts where it would on the whole frame)."""
+    _, h, w = img.shape
+    ya, yb = max(0, y0 - margin), min(h, y0 + n + margin)
+    xa, xb = max(0, x0 - margin), min(w, x0 + n + margin)
+    crop = np.ascontiguousarray(img[:, ya:yb, xa:xb])
+    want = oracle.local_laplacian(crop, 8, 1.0 / 7.0, 1.0, in_mins=(xa, ya, 0), out_mins=(xa, ya, 0))
+    w_reg = want[:, y0 - ya:y0 - ya + n, x0 - xa:x0 - xa + n]
+    g_reg = got[:, y0:y0 + n, x0:x0 + n]
+    bad = np.argwhere(g_reg != w_reg)
+    assert bad.size == 0, f"region ({y0},{x0}): {len(bad)} mismatching samples, first at {bad[0]}"
+
+
+def test_4k_interior_regions(hb, oracle):
+    """Config 2 size, away from the frame edges: where the strip / chunk / tile seams of the kernels and the balanced
+    work partition live (the corners alone never see them)."""
+    h, w = 2160, 3840
+    img = u16_frame((3, h, w), 5)
+    got = run_local_laplacian(hb, img, 8, 1.0 / 7.0, 1.0)
+    for (y0, x0) in [(1000, 1850), (1016, 3600), (37, 2001), (2032, 64)]:
+        _region_vs_oracle(oracle, img, got, y0, x0)
+
+
+def test_16k_regions(hb, oracle):
+    """North-star size (16384 x 16384 x 3): corners, an interior region, and regions straddling rows 2048*k and the
+    2^31-byte marks of the level buffers (the kernels use 32-bit element / 64-bit byte addressing at this size)."""
+    n = 16384
+    rng = np.random.default_rng(16)
+    img = rng.integers(0, 1 << 16, (3, n, n), dtype=np.uint16)
+    got = run_local_laplacian(hb, img, 8, 1.0 / 7.0, 1.0)
+    for (y0, x0) in [(0, 0), (n - 128, n - 128), (8131, 9000), (3 * 2048 - 64, 5000), (6 * 2048 - 64, 16384 - 200),
+                     (10923, 123), (16384 - 128, 7777)]:
+        _region_vs_oracle(oracle, img, got, y0, x0)
+
+
 def test_generic_kernels_agree_with_fast_path(hb, oracle):
-    """levels == 8 takes the warp-strip kernels; any other `levels` (and this hook) takes the generic
-    per-pixel kernels.  Both must equal the oracle."""
+    """levels == 8 takes the fast kernels; any other `levels` (and this hook) takes the generic per-pixel kernels.
+    Both must equal the oracle; so must every mix of them (the up-sweep then picks its planes out of the level instead
+    of the pair plane the fast down-sweep emits)."""
     img = u16_frame((3, 131, 203), 31)
     want = oracle.local_laplacian(img, 8, 1.0 / 7.0, 1.0)
     l = hb.load_library()
@@ -101,11 +140,31 @@ def test_generic_kernels_agree_with_fast_path(hb, oracle):
         l.halide_b200_ll_force_generic(0)
     got_fast = run_local_laplacian(hb, img, 8, 1.0 / 7.0, 1.0)
     assert np.array_equal(got_generic, want) and np.array_equal(got_fast, want)
+    for mask in (1, 2, 4, 8, 1 | 8, 2 | 4):
+        try:
+            l.halide_b200_ll_force_generic(mask)
+            got = run_local_laplacian(hb, img, 8, 1.0 / 7.0, 1.0)
+        finally:
+            l.halide_b200_ll_force_generic(0)
+        assert np.array_equal(got, want), f"force_generic mask {mask}"
+
+
+def test_beta_not_one_takes_the_general_kernels(hb, oracle):
+    """beta == 1 (the harness default) selects kernel variants without the beta multiply (1 * x is exact); any other
+    beta takes the general variants."""
+    img = u16_frame((3, 150, 260), 12)
+    for beta in (0.5, 1.0, 2.0):
+        _check(hb, oracle, img, 8, 1.0 / 7.0, beta)
+
+
+def test_wide_frame_many_strips(hb, oracle):
+    """A frame wide enough for several 30-column strips and 64-column tiles per row, odd sizes."""
+    _check(hb, oracle, u16_frame((3, 77, 1031), 8), 8, 1.0 / 7.0, 1.0)
 
 
 @pytest.mark.parametrize("shape", [(3, 130, 256), (3, 97, 198), (3, 64, 66)])
 def test_final_kernel_simple_and_general_layout_paths(hb, oracle, shape):
-    """Even-width 3-channel frames with 4-byte aligned rows take the final kernel's SIMPLE path (32-bit addressing,
+    """Even-width 3-channel frames with 4-byte aligned rows take the final kernel's aligned path (32-bit addressing,
     one aligned word per thread and channel); hook bit 16 forces the general-layout path on the same frame.
     Both must equal the oracle; a crop with odd column offsets must fall back to the general path by itself."""
     img = u16_frame(shape, 77)
@@ -127,18 +186,3 @@ def test_final_kernel_simple_and_general_layout_paths(hb, oracle, shape):
     want_crop = oracle.local_laplacian(img, 8, 1.0 / 7.0, 1.0, out_shape=out_shape, in_mins=(0, 0, 0), out_mins=(6, 4, 0))
     got_crop = run_local_laplacian(hb, img, 8, 1.0 / 7.0, 1.0, out_shape=out_shape, in_mins=(0, 0, 0), out_mins=(6, 4, 0))
     assert np.array_equal(got_crop, want_crop)
-
-
-@pytest.mark.parametrize("shape", [(3, 131, 203), (3, 130, 256), (3, 64, 66), (3, 257, 1031)])
-def test_pair_column_level1_kernel(hb, oracle, shape):
-    """ll_level1_pair_kernel (hook bit 32; two source columns per lane): bit-exact, kept as an alternative to
-    ll_down_strip_kernel<8, true> although it measured slightly slower (tools/level1_ab.py)."""
-    img = u16_frame(shape, 91)
-    want = oracle.local_laplacian(img, 8, 1.0 / 7.0, 1.0)
-    l = hb.load_library()
-    try:
-        l.halide_b200_ll_force_generic(32)
-        got = run_local_laplacian(hb, img, 8, 1.0 / 7.0, 1.0)
-    finally:
-        l.halide_b200_ll_force_generic(0)
-    assert np.array_equal(got, want)

@@ -60,3 +60,17 @@ def test_constant_frame_4k_band(hb):
     inp = np.full((3, 540, 3840), 0.25, np.float32)
     got = run(hb, inp, 3, 7, 0.12)
     assert np.allclose(got, 0.25, rtol=1e-6)
+
+
+def test_4k_random_frame_regions(hb, oracle):
+    """Config 4 size (3840 x 2160 x 3) on a RANDOM frame: regions of the full-size result against the oracle on the crop
+    that determines them (footprint = search/2 + patch/2 = 4 px; margin 16)."""
+    h, w = 2160, 3840
+    inp = f32_frame((3, h, w), 33)
+    got = run(hb, inp, 3, 7, 0.12)
+    for (y0, x0) in [(0, 0), (h - 64, w - 64), (1000, 1900), (540 - 32, 3000)]:
+        n, m = 64, 16
+        ya, yb, xa, xb = max(0, y0 - m), min(h, y0 + n + m), max(0, x0 - m), min(w, x0 + n + m)
+        crop = np.ascontiguousarray(inp[:, ya:yb, xa:xb])
+        want = oracle.nl_means(crop, 3, 7, 0.12, in_mins=(xa, ya, 0), out_mins=(xa, ya, 0))
+        close(got[:, y0:y0 + n, x0:x0 + n], want[:, y0 - ya:y0 - ya + n, x0 - xa:x0 - xa + n])

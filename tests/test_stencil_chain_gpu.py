@@ -44,3 +44,17 @@ def test_harness_size_linearity(hb):
     b = u16_frame((2560, 1536), 2)
     fa, fb, fab = run(hb, a), run(hb, b), run(hb, (a + b).astype(np.uint16))
     assert np.array_equal(fab, (fa + fb).astype(np.uint16))
+
+
+def test_harness_size_regions_vs_oracle(hb, oracle):
+    """1536 x 2560 (the harness frame) against the oracle by region: 32 stages of a 5x5 stencil reach 64 px, so the
+    oracle on a crop with an 80 px margin (ending exactly at the frame edges it touches) determines the region."""
+    h, w = 2560, 1536
+    inp = u16_frame((h, w), 4)
+    got = run(hb, inp)
+    for (y0, x0) in [(0, 0), (h - 96, w - 96), (1200, 700), (2048 - 48, 1024 - 48)]:
+        n, m = 96, 80
+        ya, yb, xa, xb = max(0, y0 - m), min(h, y0 + n + m), max(0, x0 - m), min(w, x0 + n + m)
+        crop = np.ascontiguousarray(inp[ya:yb, xa:xb])
+        want = oracle.stencil_chain(crop, in_mins=(xa, ya), out_mins=(xa, ya))
+        assert np.array_equal(got[y0:y0 + n, x0:x0 + n], want[y0 - ya:y0 - ya + n, x0 - xa:x0 - xa + n])
