@@ -12,7 +12,9 @@
 // column strip; each lane produces 8 adjacent pixels (one 16-byte store) per row and walks down
 // the strip keeping the last three blur_x rows in registers, so every input element is fetched
 // once per strip as part of an aligned 16-byte load and the 2-pixel horizontal apron comes from
-// the neighbouring lane by shuffle, not from memory.
+// the neighbouring lane by shuffle, not from memory.  Three input rows are requested ahead of their use.
+// (A TMA tile loader does not fit this filter's contract: cp.async.bulk.tensor needs 16-byte row strides, and the
+// harness / RunGen frames are dense rows of W + 2 uint16 — 1922, 2568+..., 7682 — which are not.)
 #include "hb_common.h"
 
 namespace {
@@ -120,11 +122,18 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) blur3x3_u16_kernel(BlurAr
     uint32_t r0[8], r1[8], r2[8];
     blur_x_row(load_raw_row(a, (int64_t)y0 * a.in_stride_y, x0, lane), lane, r0);
     blur_x_row(load_raw_row(a, (int64_t)(y0 + 1) * a.in_stride_y, x0, lane), lane, r1);
-    RawRow next = load_raw_row(a, (int64_t)(y0 + 2) * a.in_stride_y, x0, lane);
+    // three input rows in flight per lane (48 bytes): a streaming kernel needs ~30 KB of loads outstanding per SM to
+    // cover HBM latency at full bandwidth, and the resident warps alone (one row each) supplied about a third of that
+    const int last_in = y1 + 1;  // last input row this warp reads
+    RawRow q0 = load_raw_row(a, (int64_t)(y0 + 2) * a.in_stride_y, x0, lane), q1 = q0, q2 = q0;
+    if (y0 + 3 <= last_in) q1 = load_raw_row(a, (int64_t)(y0 + 3) * a.in_stride_y, x0, lane);
+    if (y0 + 4 <= last_in) q2 = load_raw_row(a, (int64_t)(y0 + 4) * a.in_stride_y, x0, lane);
     int xl = x0 + lane * kPxPerLane;
     for (int y = y0; y < y1; y++) {
-        const RawRow cur = next;
-        if (y + 1 < y1) next = load_raw_row(a, (int64_t)(y + 3) * a.in_stride_y, x0, lane);
+        const RawRow cur = q0;
+        q0 = q1;
+        q1 = q2;
+        if (y + 5 <= last_in) q2 = load_raw_row(a, (int64_t)(y + 5) * a.in_stride_y, x0, lane);
         blur_x_row(cur, lane, r2);
         uint32_t o[8];
 #pragma unroll
@@ -206,7 +215,7 @@ extern "C" int halide_blur(halide_buffer_t *input, halide_buffer_t *blur_y) {
     // two-row vertical apron.
     int strips_x = (w + kStripW - 1) / kStripW;
     int rows = 32;
-    while (rows > 4 && (int64_t)strips_x * ((h + rows - 1) / rows) < 148 * 8) rows >>= 1;
+    while (rows > 8 && (int64_t)strips_x * ((h + rows - 1) / rows) < 148 * 8) rows >>= 1;
     a.rows_per_warp = rows;
     int warps_y = (h + rows - 1) / rows;
     dim3 grid(strips_x, (warps_y + kWarpsPerBlock - 1) / kWarpsPerBlock);

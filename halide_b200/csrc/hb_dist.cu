@@ -1,15 +1,10 @@
-// hb_dist.cu — one-process-per-GPU plumbing for the row-sharded pipelines.
+// hb_dist.cu — one-process-per-GPU plumbing for the row-sharded local_laplacian.
 //
-// The reference has no distributed layer at all (SURVEY.md §2b "Collectives: none"); row-sharding with
-// halo exchange is new work.  Ranks are laid out top to bottom over the frame's rows.
-// Two transports:
-//   * peer memory (default): producers store boundary rows straight into the neighbours' CUDA-IPC-mapped slabs and
-//     handshake through release/acquire flags (PeerIO in ll_kernels.cuh); this file holds the two helper kernels that
-//     are not fused into a pipeline kernel — peer_exchange_kernel (the caller-owned input rows) and peer_gather_kernel
-//     (all-to-all gather of one coarse pyramid level) — both bounded-spin so a protocol bug reports instead of hanging;
-//   * NCCL groups (HALIDE_B200_HALO=nccl): one ncclGroup{send up, recv up, send down, recv down} per level on the
-//     compute stream.
-// NCCL is also the bootstrap for the peer path (all-gather of the IPC handles and slab layouts).
+// The reference has no distributed layer at all (SURVEY.md §2b "Collectives: none"); row-sharding is new work
+// (SURVEY.md §8e).  Ranks are laid out top to bottom over the frame's rows.  A sharded call communicates twice
+// (DESIGN.md §7): one exchange of input halo rows with the two row neighbours and one all-to-all gather of a coarse
+// pyramid level — each ONE ncclGroup of ncclSend / ncclRecv on the compute stream (`exchange`).  The bands of all ranks
+// are gathered once per geometry with `allgather_bytes`.
 //
 // NCCL is bound at run time (dlopen "libnccl.so.2") so the library has no link-time dependency and
 // shares the NCCL instance torch already loaded when the host process is the Python bench/test.
@@ -111,115 +106,6 @@ int allgather_bytes(const void *send, void *recv_all, size_t bytes) {
     cudaFree(dsend);
     cudaFree(drecv);
     return r;
-}
-
-namespace {
-
-__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__global__ void __launch_bounds__(256) peer_exchange_kernel(PeerXchg x) {
-    // 1. push: grid-stride copy of every segment into the neighbour's memory (16-byte or 2-byte elements)
-    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    for (int i = 0; i < x.nseg; i++) {
-        const PeerSeg &g = x.seg[i];
-        if (g.elem == 16) {
-            const uint4 *s = reinterpret_cast<const uint4 *>(g.src);
-            uint4 *d = reinterpret_cast<uint4 *>(g.dst);
-            for (unsigned k = tid; k < g.bytes / 16; k += nth) d[k] = s[k];
-        } else {
-            const unsigned short *s = reinterpret_cast<const unsigned short *>(g.src);
-            unsigned short *d = reinterpret_cast<unsigned short *>(g.dst);
-            for (unsigned k = tid; k < g.bytes / 2; k += nth) d[k] = s[k];
-        }
-    }
-    // 2. announce: the last block to finish its slice releases the flags in the neighbours' memory
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned prev = atomicAdd(x.done_counter, 1u);
-        if (prev == gridDim.x - 1) {
-            *x.done_counter = 0u;
-            __threadfence_system();
-            if (x.peer_flag[0]) st_release_sys(x.peer_flag[0], x.epoch);
-            if (x.peer_flag[1]) st_release_sys(x.peer_flag[1], x.epoch);
-            for (int i = 0; i < x.nready; i++) st_release_sys(x.ready_flag[i], x.epoch);
-        }
-    }
-    // 3. wait for the neighbours' rows of this step (block 0 only; bounded spin so a protocol bug cannot hang the GPU)
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        for (int d = 0; d < 2; d++) {
-            if (!x.my_flag[d]) continue;
-            long long t0 = clock64();
-            while ((int)(ld_acquire_sys(x.my_flag[d]) - x.epoch) < 0) {  // epochs only grow
-                if (clock64() - t0 > 4000000000LL) {  // ~2 s
-                    *x.error_flag = 1u;
-                    break;
-                }
-                __nanosleep(100);
-            }
-        }
-        __threadfence_system();
-    }
-}
-
-__device__ __forceinline__ void spin_until(const unsigned *flag, unsigned epoch, unsigned *error_flag) {
-    long long t0 = clock64();
-    while ((int)(ld_acquire_sys(flag) - epoch) < 0) {  // epochs only grow
-        if (clock64() - t0 > 4000000000LL) {            // ~2 s: report instead of hanging the GPU
-            *error_flag = 1u;
-            break;
-        }
-        __nanosleep(100);
-    }
-}
-
-__global__ void __launch_bounds__(256) peer_gather_kernel(PeerGather x) {
-    // 0. no peer's copy may be overwritten before that peer has drained its previous call
-    if ((int)threadIdx.x < x.npeer) spin_until(x.ready[threadIdx.x], x.epoch, x.error_flag);
-    __syncthreads();
-    // 1. push my rows into every peer's copy (16-byte elements; rows are 16-byte multiples)
-    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    for (int i = 0; i < x.nseg; i++) {
-        const PeerSeg &g = x.seg[i];
-        const uint4 *s = reinterpret_cast<const uint4 *>(g.src);
-        uint4 *d = reinterpret_cast<uint4 *>(g.dst);
-        for (unsigned k = tid; k < g.bytes / 16; k += nth) d[k] = s[k];
-    }
-    // 2. the last block to finish announces the rows to every peer
-    __threadfence_system();
-    __syncthreads();
-    __shared__ bool s_last;
-    if (threadIdx.x == 0) {
-        unsigned prev = atomicAdd(x.done_counter, 1u);
-        s_last = prev == gridDim.x - 1;
-        if (s_last) {
-            *x.done_counter = 0u;
-            __threadfence_system();
-        }
-    }
-    __syncthreads();
-    if (s_last) {
-        if ((int)threadIdx.x < x.npeer) st_release_sys(x.peer_flag[threadIdx.x], x.epoch);
-        // 3. ... and waits for theirs; the kernel boundary then orders the gathered rows before the consumers
-        if ((int)threadIdx.x < x.npeer) spin_until(x.my_flag[threadIdx.x], x.epoch, x.error_flag);
-        __threadfence_system();
-    }
-}
-
-}  // namespace
-
-void launch_peer_exchange(const PeerXchg &x, cudaStream_t s) {
-    HB_LAUNCH("peer_exchange", peer_exchange_kernel, 8, 256, 0, s, x);
-}
-void launch_peer_gather(const PeerGather &g, cudaStream_t s) {
-    HB_LAUNCH("peer_gather", peer_gather_kernel, 64, 256, 0, s, g);
 }
 
 }  // namespace hbdist

@@ -27,7 +27,7 @@ namespace {
 using namespace llk;
 
 int g_shard_coarse_level = 0;  // halide_b200_ll_shard_coarse_level: 0 = choose by size, n >= 2 = gather level n
-int g_force_naive = 0;  // test hook bitmask (halide_b200_ll_force_generic): 1 = generic down kernels, 2 = generic up, 4 = generic final, 8 = no fused coarse launch, 16 = general-layout final kernel
+int g_force_naive = 0;  // test hook bitmask (halide_b200_ll_force_generic): 1 = generic down kernels, 2 = generic up, 4 = generic final, 8 = no fused coarse launch, 16 = general-layout final kernel, 64 = no TMA frame tile in the final kernel, 128 = cooperative grid kernel instead of the cluster kernel for the coarse tail
 
 const hb::ArgSpec kIn = {"input", halide_type_uint, 16, 3, false};
 const hb::ArgSpec kOut = {"output", halide_type_uint, 16, 3, true};
@@ -214,29 +214,25 @@ int resident_slots(Kern kern, int threads, size_t smem) {
     return sms * per_sm;
 }
 
-template<bool FROM_INPUT, bool BETA1>
-void launch_down_pq(Plan &p, int j, cudaStream_t s) {
+template<bool BETA1>
+void launch_level1(Plan &p, cudaStream_t s) {
     LevelBuf *lb = p.ls.lv;
     const LLFrame &f = p.f;
-    const size_t smem = FROM_INPUT ? kLutPad * sizeof(float) + kDWarps * sizeof(DownStage) : 0;
+    const size_t smem = kLutPad * sizeof(float) + kDWarps * sizeof(DownStage);
     // (the attribute and the occupancy are per device and cheap to query; no process-wide caching)
-    const int slots = resident_slots(ll_down_pq_kernel<FROM_INPUT, BETA1>, kDWarps * 32, smem);
-    const int ns = (lb[j].sx.n() + kDCols - 1) / kDCols, nc = (lb[j].cy.n() + kDR - 1) / kDR;
+    const int slots = resident_slots(ll_level1_kernel<BETA1>, kDWarps * 32, smem);
+    const int ns = (lb[1].sx.n() + kDCols - 1) / kDCols, nc = (lb[1].cy.n() + kDR - 1) / kDR;
     const long long units = (long long)ns * nc;
     // one block per resident slot, but never fewer than ~2 units per warp's worth of work per block
     long long g = (units + 1) / 2;
     if (g > slots) g = slots;
     if (g < 1) g = 1;
-    int wide = 0;
-    // the whole input addressable with 32-bit element offsets from its first element (positive strides)
+    // aligned 32-bit loads of a column pair / 32-bit element offsets from the buffer's first element
+    const int wide = ((uintptr_t)f.in & 3) == 0 && (f.in_sy & 1) == 0 && (f.in_sc & 1) == 0 && (f.in_x0 & 1) == 0 &&
+                     ((uintptr_t)f.halo_top & 3) == 0 && ((uintptr_t)f.halo_bot & 3) == 0 && (f.halo_pitch & 1) == 0;
     const int idx32 = f.in_sy > 0 && f.in_sc > 0 && (int64_t)f.in_h * f.in_sy + (int64_t)f.in_c * f.in_sc < (1ll << 31);
-    if (FROM_INPUT) {
-        wide = ((uintptr_t)f.in & 3) == 0 && (f.in_sy & 1) == 0 && (f.in_sc & 1) == 0 && (f.in_x0 & 1) == 0 &&
-               ((uintptr_t)f.halo_top & 3) == 0 && ((uintptr_t)f.halo_bot & 3) == 0 && (f.halo_pitch & 1) == 0;
-    }
-    HB_LAUNCH(FROM_INPUT ? "ll_level1_pq" : "ll_down_pq", (ll_down_pq_kernel<FROM_INPUT, BETA1>), (int)g, kDWarps * 32, smem, s, p.f,
-              lb[j - 1], lb[j], ns, nc, wide, idx32);
-    lb[j].has_pair = 1;
+    HB_LAUNCH("ll_level1", (ll_level1_kernel<BETA1>), (int)g, kDWarps * 32, smem, s, p.f, lb[1], ns, nc, wide, idx32);
+    lb[1].has_pair = 1;
 }
 
 void launch_down(Plan &p, int j, cudaStream_t s) {  // produce level j (j >= 1) rows cy
@@ -246,8 +242,8 @@ void launch_down(Plan &p, int j, cudaStream_t s) {  // produce level j (j >= 1) 
     if (fast) {
         const bool beta1 = p.f.beta == 1.0f;
         if (j == 1) {
-            if (beta1) launch_down_pq<true, true>(p, j, s);
-            else launch_down_pq<true, false>(p, j, s);
+            if (beta1) launch_level1<true>(p, s);
+            else launch_level1<false>(p, s);
         } else {
             // stored levels: load-bound row-group kernel; no pair plane (the up-sweep of these small levels picks its two
             // planes out of the level itself)
@@ -259,7 +255,7 @@ void launch_down(Plan &p, int j, cudaStream_t s) {  // produce level j (j >= 1) 
             HB_LAUNCH("ll_down_rows", ll_down_rows_kernel, (int)g, 256, 0, s, lb[j - 1], lb[j], ns, ng);
         }
     } else if (j == 1) {
-        HB_LAUNCH("ll_level1", ll_level1_naive_kernel, grid_for(lb[1].sx.n(), lb[1].cy.n()), kBlk, 0, s, p.f, lb[1]);
+        HB_LAUNCH("ll_level1_generic", ll_level1_naive_kernel, grid_for(lb[1].sx.n(), lb[1].cy.n()), kBlk, 0, s, p.f, lb[1]);
     } else {
         HB_LAUNCH("ll_down", ll_down_naive_kernel, grid_for(lb[j].sx.n(), lb[j].cy.n()), kBlk, 0, s, lb[j - 1], lb[j], p.K);
     }
@@ -274,8 +270,9 @@ void launch_up(Plan &p, int j, cudaStream_t s) {  // produce outGPyramid[j] (1 <
     if (lb[j].coy.n() <= 0) return;
     const bool fast_up = (p.K == 8) && !(g_force_naive & 2);
     if (fast_up && j < p.J - 1) {
-        HB_LAUNCH("ll_up2", (ll_up2_kernel<false, false, true>), up_grid(lb[j].ox.lo, lb[j].ox.hi, lb[j].coy.lo, lb[j].coy.hi), 256, 0, s,
-                  p.f, lb[j], lb[j + 1]);
+        static const CUtensorMap no_map = {};
+        HB_LAUNCH("ll_up2", (ll_up2_kernel<false, false, true>), up_grid(lb[j].ox.lo, lb[j].ox.hi, lb[j].coy.lo, lb[j].coy.hi), 256,
+                  up2_smem_bytes(false, false), s, p.f, lb[j], lb[j + 1], no_map);
     } else {
         HB_LAUNCH("ll_up", ll_up_naive_kernel, grid_for(lb[j].ox.n(), lb[j].coy.n()), kBlk, 0, s, lb[j],
                   lb[j == p.J - 1 ? j : j + 1], p.f.flm1, p.f.levels, j == p.J - 1 ? 1 : 0);
@@ -296,15 +293,29 @@ void launch_final(Plan &p, cudaStream_t s) {
                              f.in_sy > 0 && f.in_sc > 0 && f.out_sy > 0 && f.out_sc > 0 && in_span < (1ll << 31) &&
                              out_span < (1ll << 31) && !(g_force_naive & 16);
         const bool beta1 = f.beta == 1.0f;
-        if (aligned && beta1) {
-            HB_LAUNCH("ll_final2", (ll_up2_kernel<true, true, true>), g, 256, 0, s, p.f, lb[1], lb[1]);
-        } else if (aligned) {
-            HB_LAUNCH("ll_final2", (ll_up2_kernel<true, true, false>), g, 256, 0, s, p.f, lb[1], lb[1]);
-        } else if (beta1) {
-            HB_LAUNCH("ll_final2", (ll_up2_kernel<true, false, true>), g, 256, 0, s, p.f, lb[1], lb[1]);
-        } else {
-            HB_LAUNCH("ll_final2", (ll_up2_kernel<true, false, false>), g, 256, 0, s, p.f, lb[1], lb[1]);
+        // frame tile by TMA when the buffer meets TMA's rules (16-byte aligned base and strides); the map describes the
+        // input buffer itself (x, y, c), so a tile reaching past it reads zeros for pixels that are never stored
+        CUtensorMap in_map = {};
+        bool use_tma = false;
+        if (aligned && !(g_force_naive & 64)) {
+            const int64_t strides[2] = {f.in_sy * 2, f.in_sc * 2};
+            if (tma::strides_ok(f.in, strides, 2)) {
+                const uint64_t dims[3] = {(uint64_t)f.in_w, (uint64_t)f.in_h, (uint64_t)f.in_c};
+                const uint32_t box[3] = {kUpTW, kUpTH, 3};
+                use_tma = tma::encode(&in_map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, (void *)f.in, dims, strides, box);
+            }
         }
+        auto launch = [&](auto kern, bool tma_on) {
+            const int smem = up2_smem_bytes(true, tma_on);
+            if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  // (per device, cheap)
+            HB_LAUNCH("ll_final2", kern, g, 256, smem, s, p.f, lb[1], lb[1], in_map);
+        };
+        if (use_tma && beta1) launch(ll_up2_kernel<true, true, true, true>, true);
+        else if (use_tma) launch(ll_up2_kernel<true, true, false, true>, true);
+        else if (aligned && beta1) launch(ll_up2_kernel<true, true, true, false>, false);
+        else if (aligned) launch(ll_up2_kernel<true, true, false, false>, false);
+        else if (beta1) launch(ll_up2_kernel<true, false, true, false>, false);
+        else launch(ll_up2_kernel<true, false, false, false>, false);
     } else {
         HB_LAUNCH("ll_final", ll_final_naive_kernel, grid_for(p.f.W, p.f.nrows), kBlk, 0, s, p.f, lb[1], p.J > 1 ? 1 : 0);
     }
@@ -332,19 +343,40 @@ bool launch_coarse_fused(Plan &p, int j0, cudaStream_t s) {
     return true;
 }
 
+// The smallest levels as one thread-block cluster (see ll_coarse_cluster_kernel): levels j0+1 .. J-1 down and up.
+bool launch_coarse_cluster(Plan &p, int j0, cudaStream_t s) {
+    int J = p.J, K = p.K, levels = p.f.levels;
+    float flm1 = p.f.flm1;
+    hb::count_launch("ll_coarse_cluster", s);
+    ll_coarse_cluster_kernel<<<kClusterCtas, kClusterThreads, 0, s>>>(p.ls, J, j0, K, flm1, levels);
+    hb::after_launch(s);
+    if (cudaGetLastError() != cudaSuccess) return false;
+    return true;
+}
+
 // Levels from_level+1 .. J-1 down, then J-1 .. from_level+1 up: the part of the sweep that runs on whole levels
-// (everything on one GPU; the replicated coarse levels when row-sharded).  Small levels share one cooperative launch.
+// (everything on one GPU; the replicated coarse levels when row-sharded).  Levels of a few thousand pixels share one
+// launch: a thread-block cluster for the smallest ones, else (hook bit 128, or when the cluster launch is refused) the
+// cooperative grid kernel for everything up to 40 K pixels.
 void run_coarse_sweep(Plan &p, int from_level, cudaStream_t s) {
-    int j0 = p.J - 1;
-    if (!(g_force_naive & 8)) {
-        // (level 1 always has its own launch: it is built from the frame, not from a stored level)
-        const int j_min = from_level < 1 ? 1 : from_level;
-        while (j0 > j_min && (int64_t)p.ls.lv[j0].sx.n() * p.ls.lv[j0].sy.n() <= 40 * 1024) j0--;
-    }
-    // j0 = last level produced by its own launch; levels j0+1.. are fused (if any)
+    // (level 1 always has its own launch: it is built from the frame, not from a stored level)
+    const int j_min = from_level < 1 ? 1 : from_level;
+    auto px = [&](int j) { return (int64_t)p.ls.lv[j].sx.n() * p.ls.lv[j].sy.n(); };
+    int j0 = p.J - 1;  // last level produced by its own launch; levels j0+1.. are fused (if any)
     bool fused = false;
-    for (int j = from_level + 1; j <= j0; j++) launch_down(p, j, s);
-    if (j0 < p.J - 1) fused = launch_coarse_fused(p, j0, s);
+    if (!(g_force_naive & 8)) {
+        if (!(g_force_naive & 128)) {
+            while (j0 > j_min && px(j0) <= 12 * 1024) j0--;
+            for (int j = from_level + 1; j <= j0; j++) launch_down(p, j, s);
+            if (j0 < p.J - 1) fused = launch_coarse_cluster(p, j0, s);
+        } else {
+            while (j0 > j_min && px(j0) <= 40 * 1024) j0--;
+            for (int j = from_level + 1; j <= j0; j++) launch_down(p, j, s);
+            if (j0 < p.J - 1) fused = launch_coarse_fused(p, j0, s);
+        }
+    } else {
+        for (int j = from_level + 1; j <= j0; j++) launch_down(p, j, s);
+    }
     if (!fused) {
         for (int j = j0 + 1; j < p.J; j++) launch_down(p, j, s);
         for (int j = p.J - 1; j > j0; j--) launch_up(p, j, s);

@@ -65,6 +65,17 @@ static inline float lerpf(float zero_val, float one_val, float w) {
 static inline float recip_const(float c) {
     return (float)(1.0 / (double)c);
 }
+// x / c for a constant c.  Default ("target=host", apps/support/Makefile.inc:22): the simplifier rewrites it to
+// x * fold(1/c) (src/Simplify_Div.cpp:204).  With -DORACLE_STRICT_FLOAT the oracle restates a `strict_float` build
+// (src/Target.cpp:603, src/StrictifyFloat.cpp:10-60), where that rewrite does not fire and the division is a true IEEE
+// divide — the flag to flip the day a contraction-free Halide build exists to diff against.
+static inline float div_const(float x, float c) {
+#ifdef ORACLE_STRICT_FLOAT
+    return x / c;
+#else
+    return x * recip_const(c);
+#endif
+}
 
 // High-order coefficient first; n = number of coefficients (degree + 1).
 static inline float evaluate_polynomial(float x, const float *coeff, int n) {
@@ -143,7 +154,7 @@ static inline float halide_pow(float x, float y) {
 
 static inline float fast_exp(float x_full) {
     const float ln2 = logf(2.0f);
-    float scaled = x_full * recip_const(ln2);
+    float scaled = div_const(x_full, ln2);
     float k_real = floorf(scaled);
     int32_t k = (int32_t)k_real;
     float x = x_full - k_real * ln2;

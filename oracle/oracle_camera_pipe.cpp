@@ -42,7 +42,7 @@ extern "C" void oracle_camera_pipe_tables(const float *m3200, const float *m7000
                                           uint8_t *curve1024, uint8_t *s32_out) {
     // matrix(x,y) = i16((m3200*alpha + m7000*(1-alpha)) * 256) (generator :268-271); x in [0,4), y in [0,3)
     const float c3200 = 1.0f / 3200, c7000 = 1.0f / 7000;
-    const float alpha = (1.0f / color_temp - c3200) * hl::recip_const(c7000 - c3200);
+    const float alpha = hl::div_const(1.0f / color_temp - c3200, c7000 - c3200);
     for (int i = 0; i < 12; i++) {
         float val = m3200[i] * alpha + m7000[i] * (1.0f - alpha);
         matrix12[i] = (int16_t)(val * 256.0f);
@@ -50,7 +50,7 @@ extern "C" void oracle_camera_pipe_tables(const float *m3200, const float *m7000
     // tone curve (generator :301-332)
     const int minRaw = 0 + blackLevel, maxRaw = whiteLevel;
     const float invRange = 1.0f / (float)(maxRaw - minRaw);
-    const float b = 2.0f - hl::halide_pow(2.0f, contrast * hl::recip_const(100.0f));
+    const float b = 2.0f - hl::halide_pow(2.0f, hl::div_const(contrast, 100.0f));
     const float a = 2.0f - 2.0f * b;
     const float inv_gamma = 1.0f / gamma;
     for (int x = 0; x < 1024; x++) {

@@ -121,7 +121,6 @@ extern "C" int oracle_local_laplacian(const oracle_image_t *in, int levels, floa
     std::vector<float> lut(2 * lut_half + 1);
     for (int i = -lut_half; i <= lut_half; i++) lut[i + lut_half] = oracle_ll_remap(i, alpha);
 
-    const float inv65535 = hl::recip_const(65535.0f);
     const float flm1 = (float)(levels - 1);
     const float inv_lm1 = 1.0f / flm1;
 
@@ -131,9 +130,9 @@ extern "C" int oracle_local_laplacian(const oracle_image_t *in, int levels, floa
 #pragma omp parallel for schedule(static)
     for (int y = GY[0].lo; y <= GY[0].hi; y++) {
         for (int x = GX[0].lo; x <= GX[0].hi; x++) {
-            const float f0 = (float)in_clamped(x, y, 0) * inv65535;
-            const float f1 = (float)in_clamped(x, y, 1) * inv65535;
-            const float f2 = (float)in_clamped(x, y, 2) * inv65535;
+            const float f0 = hl::div_const((float)in_clamped(x, y, 0), 65535.0f);
+            const float f1 = hl::div_const((float)in_clamped(x, y, 1), 65535.0f);
+            const float f2 = hl::div_const((float)in_clamped(x, y, 2), 65535.0f);
             gray.at(x, y, 0) = (0.299f * f0 + 0.587f * f1) + 0.114f * f2;
         }
     }

@@ -48,6 +48,16 @@ def lib():
     return _lib
 
 
+def strict_float_lib():
+    """The same oracle built with -DORACLE_STRICT_FLOAT (constant divisions stay IEEE divides, as in a Halide
+    `strict_float` build; halide_math.h: div_const).  Not the parity target: kept for diffing against a future
+    contraction-free Halide build."""
+    path = os.path.join(_HERE, "liboracle_strict.so")
+    if not os.path.exists(path):
+        build()
+    return ctypes.CDLL(path)
+
+
 def image(arr, mins=None):
     """Describe a numpy array (outermost-first indexing) as an oracle_image_t."""
     img = oracle_image_t()
