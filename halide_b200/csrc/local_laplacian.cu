@@ -27,7 +27,7 @@ namespace {
 using namespace llk;
 
 int g_shard_coarse_level = 0;  // halide_b200_ll_shard_coarse_level: 0 = choose by size, n >= 2 = gather level n
-int g_force_naive = 0;  // test hook bitmask (halide_b200_ll_force_generic): 1 = generic down kernels, 2 = generic up, 4 = generic final, 8 = no fused coarse launch, 16 = general-layout final kernel, 64 = no TMA frame tile in the final kernel, 128 = cooperative grid kernel instead of the cluster kernel for the coarse tail
+int g_force_naive = 0;  // test hook bitmask (halide_b200_ll_force_generic): 1 = generic down kernels, 2 = generic up, 4 = generic final, 8 = no fused coarse launch, 16 = general-layout final kernel, 64 = no TMA frame tile in the final kernel
 
 const hb::ArgSpec kIn = {"input", halide_type_uint, 16, 3, false};
 const hb::ArgSpec kOut = {"output", halide_type_uint, 16, 3, true};
@@ -299,9 +299,10 @@ void launch_final(Plan &p, cudaStream_t s) {
         bool use_tma = false;
         if (aligned && !(g_force_naive & 64)) {
             const int64_t strides[2] = {f.in_sy * 2, f.in_sc * 2};
-            if (tma::strides_ok(f.in, strides, 2)) {
+            // (every tile's first column must also start on a 16-byte boundary: crops at other even offsets take the load path)
+            if (tma::strides_ok(f.in, strides, 2) && (((f.out_x0 & ~1) - f.in_x0) & 7) == 0) {
                 const uint64_t dims[3] = {(uint64_t)f.in_w, (uint64_t)f.in_h, (uint64_t)f.in_c};
-                const uint32_t box[3] = {kUpTW, kUpTH, 3};
+                const uint32_t box[3] = {kUpInW, kUpTH, 3};
                 use_tma = tma::encode(&in_map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, (void *)f.in, dims, strides, box);
             }
         }
@@ -328,7 +329,14 @@ bool launch_coarse_fused(Plan &p, int j0, cudaStream_t s) {
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ll_coarse_fused_kernel, 256, 0);
-    const int max_blocks = coop ? sms * (per_sm > 2 ? 2 : per_sm) : 0;
+    // one or two blocks per SM (HALIDE_B200_LL_COOP_BLOCKS_PER_SM): fewer blocks make the grid barriers cheaper, more
+    // threads shorten the phases between them
+    static const int want_per_sm = [] {
+        const char *e = getenv("HALIDE_B200_LL_COOP_BLOCKS_PER_SM");
+        const int v = e ? atoi(e) : 2;
+        return v < 1 ? 1 : (v > 4 ? 4 : v);
+    }();
+    const int max_blocks = coop ? sms * (per_sm > want_per_sm ? want_per_sm : per_sm) : 0;
     if (max_blocks <= 0) return false;
     int J = p.J, K = p.K, levels = p.f.levels;
     float flm1 = p.f.flm1;
@@ -343,40 +351,22 @@ bool launch_coarse_fused(Plan &p, int j0, cudaStream_t s) {
     return true;
 }
 
-// The smallest levels as one thread-block cluster (see ll_coarse_cluster_kernel): levels j0+1 .. J-1 down and up.
-bool launch_coarse_cluster(Plan &p, int j0, cudaStream_t s) {
-    int J = p.J, K = p.K, levels = p.f.levels;
-    float flm1 = p.f.flm1;
-    hb::count_launch("ll_coarse_cluster", s);
-    ll_coarse_cluster_kernel<<<kClusterCtas, kClusterThreads, 0, s>>>(p.ls, J, j0, K, flm1, levels);
-    hb::after_launch(s);
-    if (cudaGetLastError() != cudaSuccess) return false;
-    return true;
-}
-
 // Levels from_level+1 .. J-1 down, then J-1 .. from_level+1 up: the part of the sweep that runs on whole levels
-// (everything on one GPU; the replicated coarse levels when row-sharded).  Levels of a few thousand pixels share one
-// launch: a thread-block cluster for the smallest ones, else (hook bit 128, or when the cluster launch is refused) the
-// cooperative grid kernel for everything up to 40 K pixels.
+// (everything on one GPU; the replicated coarse levels when row-sharded).  Small levels share one cooperative launch.
+// (Tried and dropped: the levels of <= 12 K pixels as one 8-CTA thread-block cluster with hardware cluster barriers
+// instead of grid barriers — 41 us against 35 us for the cooperative kernel at 4K: eight SMs' worth of threads cannot
+// cover the L2 latency of these phases, the barriers were not the cost.)
 void run_coarse_sweep(Plan &p, int from_level, cudaStream_t s) {
-    // (level 1 always has its own launch: it is built from the frame, not from a stored level)
-    const int j_min = from_level < 1 ? 1 : from_level;
-    auto px = [&](int j) { return (int64_t)p.ls.lv[j].sx.n() * p.ls.lv[j].sy.n(); };
-    int j0 = p.J - 1;  // last level produced by its own launch; levels j0+1.. are fused (if any)
-    bool fused = false;
+    int j0 = p.J - 1;
     if (!(g_force_naive & 8)) {
-        if (!(g_force_naive & 128)) {
-            while (j0 > j_min && px(j0) <= 12 * 1024) j0--;
-            for (int j = from_level + 1; j <= j0; j++) launch_down(p, j, s);
-            if (j0 < p.J - 1) fused = launch_coarse_cluster(p, j0, s);
-        } else {
-            while (j0 > j_min && px(j0) <= 40 * 1024) j0--;
-            for (int j = from_level + 1; j <= j0; j++) launch_down(p, j, s);
-            if (j0 < p.J - 1) fused = launch_coarse_fused(p, j0, s);
-        }
-    } else {
-        for (int j = from_level + 1; j <= j0; j++) launch_down(p, j, s);
+        // (level 1 always has its own launch: it is built from the frame, not from a stored level)
+        const int j_min = from_level < 1 ? 1 : from_level;
+        while (j0 > j_min && (int64_t)p.ls.lv[j0].sx.n() * p.ls.lv[j0].sy.n() <= 40 * 1024) j0--;
     }
+    // j0 = last level produced by its own launch; levels j0+1.. are fused (if any)
+    bool fused = false;
+    for (int j = from_level + 1; j <= j0; j++) launch_down(p, j, s);
+    if (j0 < p.J - 1) fused = launch_coarse_fused(p, j0, s);
     if (!fused) {
         for (int j = j0 + 1; j < p.J; j++) launch_down(p, j, s);
         for (int j = p.J - 1; j > j0; j--) launch_up(p, j, s);

@@ -294,8 +294,8 @@ void halide_b200_ll_shard_coarse_level(int level);
 /* The level the sharded call gathers for a frame_w x frame_h frame over nranks ranks; host-only. */
 int halide_b200_ll_shard_plan_level(int32_t frame_w, int32_t frame_h, int32_t nranks);
 /* Test hook: bitmask routing levels==8 calls through the generic kernels (1 down, 2 up, 4 final,
- * 8 no fused coarse launch, 16 general-layout final kernel, 64 no TMA frame tile in the final kernel, 128 cooperative
- * grid kernel instead of the cluster kernel for the coarse tail) so every code path stays covered by the parity tests. */
+ * 8 no fused coarse launch, 16 general-layout final kernel, 64 no TMA frame tile in the final
+ * kernel) so every code path stays covered by the parity tests. */
 void halide_b200_ll_force_generic(int mask);
 /* conv_layer: 1 = tcgen05/TMEM/TMA implicit GEMM (3xTF32 split), 0 = FP32 SIMT kernel (also HALIDE_B200_CONV=tc|simt). */
 void halide_b200_conv_use_tensor_cores(int enable);
