@@ -38,6 +38,7 @@ WORKLOADS = {
     # name: (W, H) of the whole frame
     "local_laplacian_16k": (16384, 16384),
     "local_laplacian_8k": (7680, 4320),
+    "local_laplacian_16k_quarter": (16384, 4096),   # what one rank of four sees (diagnostics)
     "local_laplacian_4k": (3840, 2160),
 }
 DEFAULT_WORKLOAD = "local_laplacian_16k"

@@ -13,8 +13,9 @@
 //                   conflicts: bin-major layout), the two lanes of a cell then emit blurz.
 //   bg_blur_xy      blurx then blury fused: each thread owns one (cell column, z, channel) and walks
 //                   down the grid rows with a 5-row register window of blurx values.
-//   bg_slice        4 pixels per thread (float4 in / float4 out), 8 float2 grid gathers per pixel
-//                   served by L1/L2 (the grid is ~0.4 B/px).
+//   bg_slice        one block per 120 x 8 pixels (one row of grid cells): the 16 x 2 x nz cells it interpolates between
+//                   are staged in shared memory with a plane stride of 32 cells (bank = cell, whatever the plane);
+//                   4 pixels per thread (float4 in / float4 out), 8 shared 8-byte corner loads per pixel.
 // Grid layout in HBM: [cell_y][cell_x][z][2] f32 — the (z, z+1) x (value, weight) quad a pixel
 // needs at one corner is 16 contiguous bytes.
 #include "hb_common.h"
@@ -120,49 +121,63 @@ __global__ void __launch_bounds__(256) bg_blur_xy_kernel(BGParams p, int rows_pe
 }
 
 // ---- K3: trilinear slice + normalise -----------------------------------------------------------------
-__device__ __forceinline__ float bg_slice_px(const BGParams &p, float raw, int x, int y) {
-    float val = hl::clampf(raw, 0.0f, 1.0f);
-    float zv = __fmul_rn(val, p.inv_r);
-    int zi = (int)zv;
-    float zf = __fsub_rn(zv, (float)zi);
-    zi = min(zi, p.nz - 2);
-    float xf = __fmul_rn((float)(x & (S - 1)), 0.125f);
-    float yf = __fmul_rn((float)(y & (S - 1)), 0.125f);
-    int xi = (x >> 3) - p.gx0, yi = (y >> 3) - p.gy0;
-    const int V = p.nz * 2;
-    const float2 *c00 = reinterpret_cast<const float2 *>(p.grid_b + ((size_t)yi * p.gw + xi) * V) + zi;
-    const float2 *c01 = c00 + p.nz;                    // xi + 1
-    const float2 *c10 = c00 + (size_t)p.gw * p.nz;     // yi + 1
-    const float2 *c11 = c10 + p.nz;
-    float2 a0 = __ldg(c00), a1 = __ldg(c00 + 1), b0 = __ldg(c01), b1 = __ldg(c01 + 1);
-    float2 d0 = __ldg(c10), d1 = __ldg(c10 + 1), e0 = __ldg(c11), e1 = __ldg(c11 + 1);
-    // lerp nest x -> y -> z exactly as generator :59-64
-    float v0 = hl::lerpf(hl::lerpf(hl::lerpf(a0.x, b0.x, xf), hl::lerpf(d0.x, e0.x, xf), yf),
-                         hl::lerpf(hl::lerpf(a1.x, b1.x, xf), hl::lerpf(d1.x, e1.x, xf), yf), zf);
-    float v1 = hl::lerpf(hl::lerpf(hl::lerpf(a0.y, b0.y, xf), hl::lerpf(d0.y, e0.y, xf), yf),
-                         hl::lerpf(hl::lerpf(a1.y, b1.y, xf), hl::lerpf(d1.y, e1.y, xf), yf), zf);
-    return __fdiv_rn(v0, v1);
-}
+// One block = 120 x 8 pixels = one row of grid cells: the 16 x 2 cells (x nz planes x 2 channels) its pixels interpolate
+// between are staged once into shared memory as [z][cell] float2 with 32 cells per plane, so that a corner fetch is one
+// 8-byte shared load whose bank depends on the cell only, never on the data-dependent plane zi.  (The first version
+// gathered the eight corners of every pixel straight from L1: up to 13 cache lines per warp instruction, and the L1
+// data pipe, not HBM, was the bound — 92 % busy, profiles/r02_other_pipelines_ncu.md.)  30 of 32 lanes hold 4 pixels each.
+constexpr int kSliceW = 120, kSliceCells = 16;
 
 __global__ void __launch_bounds__(256) bg_slice_kernel(BGParams p) {
-    const int tx = blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 pixels
-    const int ty = blockIdx.y;
-    const int lx = tx * 4;
-    if (lx >= p.W) return;
-    const int y = p.out_y0 + ty, x = p.out_x0 + lx;
+    extern __shared__ float2 s_grid[];  // [nz][2 * kSliceCells]
+    const int lane = threadIdx.x, row = threadIdx.y, tid = row * 32 + lane;
+    const int X0 = (p.out_x0 & ~(S - 1)) + blockIdx.x * kSliceW, Y0 = (p.out_y0 & ~(S - 1)) + blockIdx.y * S;
+    const int cx0 = (X0 >> 3) - p.gx0, cy0 = (Y0 >> 3) - p.gy0;  // first stored cell of the tile
+    {
+        const float2 *g = reinterpret_cast<const float2 *>(p.grid_b);
+        for (int it = tid; it < 2 * kSliceCells * p.nz; it += 256) {
+            const int z = it % p.nz, cell = it / p.nz;  // (z fastest: the planes of a cell are contiguous in HBM)
+            const int cx = min(cx0 + (cell & (kSliceCells - 1)), p.gw - 1), cy = min(cy0 + (cell >> 4), p.gh - 1);
+            s_grid[z * (2 * kSliceCells) + cell] = __ldg(g + ((size_t)cy * p.gw + cx) * p.nz + z);
+        }
+    }
+    __syncthreads();
+    const int y = Y0 + row, x = X0 + 4 * lane;
+    if (lane >= kSliceW / 4 || y < p.out_y0 || y >= p.out_y0 + p.H || x + 3 < p.out_x0 || x >= p.out_x0 + p.W) return;
     const float *ip = p.in + (int64_t)(y - p.in_y0) * p.in_sy + (x - p.in_x0);
-    float *op = p.out + (int64_t)ty * p.out_sy + lx;
-    const bool full = lx + 3 < p.W;
+    float *op = p.out + (int64_t)(y - p.out_y0) * p.out_sy + (x - p.out_x0);
+    const float2 *c00 = s_grid + (lane >> 1);  // cell (xi, yi) of this thread's four pixels; xi + 1: +1, yi + 1: +kSliceCells
+    const float yf = __fmul_rn((float)(y & (S - 1)), 0.125f);
+    auto px = [&](float raw, int xx) -> float {
+        const float val = hl::clampf(raw, 0.0f, 1.0f);
+        const float zv = __fmul_rn(val, p.inv_r);
+        int zi = (int)zv;
+        const float zf = __fsub_rn(zv, (float)zi);
+        zi = min(zi, p.nz - 2);
+        const float xf = __fmul_rn((float)(xx & (S - 1)), 0.125f);
+        const float2 *c = c00 + zi * (2 * kSliceCells);
+        const float2 a0 = c[0], b0 = c[1], d0 = c[kSliceCells], e0 = c[kSliceCells + 1];
+        const float2 a1 = c[2 * kSliceCells], b1 = c[2 * kSliceCells + 1], d1 = c[3 * kSliceCells], e1 = c[3 * kSliceCells + 1];
+        // lerp nest x -> y -> z exactly as generator :59-64
+        const float v0 = hl::lerpf(hl::lerpf(hl::lerpf(a0.x, b0.x, xf), hl::lerpf(d0.x, e0.x, xf), yf),
+                                   hl::lerpf(hl::lerpf(a1.x, b1.x, xf), hl::lerpf(d1.x, e1.x, xf), yf), zf);
+        const float v1 = hl::lerpf(hl::lerpf(hl::lerpf(a0.y, b0.y, xf), hl::lerpf(d0.y, e0.y, xf), yf),
+                                   hl::lerpf(hl::lerpf(a1.y, b1.y, xf), hl::lerpf(d1.y, e1.y, xf), yf), zf);
+        return __fdiv_rn(v0, v1);
+    };
+    const bool full = x >= p.out_x0 && x + 3 < p.out_x0 + p.W;
     if (full && ((reinterpret_cast<uintptr_t>(ip) | reinterpret_cast<uintptr_t>(op)) & 15) == 0) {
-        float4 v = __ldg(reinterpret_cast<const float4 *>(ip));
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(ip));
         float4 o;
-        o.x = bg_slice_px(p, v.x, x, y);
-        o.y = bg_slice_px(p, v.y, x + 1, y);
-        o.z = bg_slice_px(p, v.z, x + 2, y);
-        o.w = bg_slice_px(p, v.w, x + 3, y);
+        o.x = px(v.x, x);
+        o.y = px(v.y, x + 1);
+        o.z = px(v.z, x + 2);
+        o.w = px(v.w, x + 3);
         *reinterpret_cast<float4 *>(op) = o;
     } else {
-        for (int i = 0; i < 4 && lx + i < p.W; i++) op[i] = bg_slice_px(p, __ldg(ip + i), x + i, y);
+        for (int i = 0; i < 4; i++) {
+            if (x + i >= p.out_x0 && x + i < p.out_x0 + p.W) op[i] = px(__ldg(ip + i), x + i);
+        }
     }
 }
 
@@ -260,8 +275,11 @@ int run_bilateral_grid(halide_buffer_t *input, float r_sigma, halide_buffer_t *o
         while (rows > 2 && (int64_t)((cols + 255) / 256) * ((p.gh - 4 + rows - 1) / rows) < 148 * 4) rows >>= 1;
         dim3 g2((cols + 255) / 256, (p.gh - 4 + rows - 1) / rows);
         HB_LAUNCH("bg_blur_xy", bg_blur_xy_kernel, g2, 256, 0, s, p, rows);
-        dim3 g3(((W + 3) / 4 + 255) / 256, H);
-        HB_LAUNCH("bg_slice", bg_slice_kernel, g3, 256, 0, s, p);
+        const int tx0 = ox & ~(S - 1), ty0 = oy & ~(S - 1);
+        dim3 g3((ox + W - tx0 + kSliceW - 1) / kSliceW, (oy + H - ty0 + S - 1) / S);
+        const size_t slice_smem = (size_t)p.nz * 2 * kSliceCells * sizeof(float2);
+        if (slice_smem > 48 * 1024) cudaFuncSetAttribute(bg_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slice_smem);
+        HB_LAUNCH("bg_slice", bg_slice_kernel, g3, dim3(32, 8), slice_smem, s, p);
     }
     if ((r = hb::check_cuda(cudaGetLastError(), "bilateral_grid launch", halide_error_code_device_run_failed))) return r;
     hb::mark_output_written(output);

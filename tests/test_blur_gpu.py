@@ -73,3 +73,24 @@ def test_blur_device_resident_buffers(hb, oracle):
     bo.device_sync()
     got = t_out.view(torch.int16).cpu().numpy().view(np.uint16)
     assert np.array_equal(got, oracle.blur(inp))
+
+
+@pytest.mark.parametrize("h,w", [(64, 128), (37, 190), (130, 257), (200, 1000)])
+def test_blur_pair_and_general_kernels(hb, oracle, h, w):
+    """Frames whose rows keep pixel pairs 4-byte aligned (even row strides) take the aligned-pair kernel; the hook routes
+    the same frame through the general (any alignment) kernel.  Both must equal the oracle; odd output widths and odd
+    column offsets (which fall back to the general kernel by themselves) included."""
+    inp = u16_frame((h + 2, w + 2 + (w & 1)), 100 + w)   # even row stride
+    want = oracle.blur(inp, out_shape=(h, w))
+    l = hb.load_library()
+    got_pair = run_blur(hb, inp, (h, w))
+    try:
+        l.halide_b200_blur_force_general(1)
+        got_general = run_blur(hb, inp, (h, w))
+    finally:
+        l.halide_b200_blur_force_general(0)
+    assert np.array_equal(got_pair, want) and np.array_equal(got_general, want)
+    # output region starting at an odd input column: general kernel by itself
+    want_off = oracle.blur(inp, out_shape=(h - 3, w - 5), in_mins=(0, 0), out_mins=(3, 2))
+    got_off = run_blur(hb, inp, (h - 3, w - 5), in_mins=(0, 0), out_mins=(3, 2))
+    assert np.array_equal(got_off, want_off)

@@ -28,7 +28,13 @@ def u16(shape, dev, g):
     return torch.randint(-32768, 32768, shape, dtype=torch.int16, device=dev, generator=g).view(torch.uint16)
 
 
+LAST_KERNELS = {}
+
+
 def time_gpu(make_sets, call, steps, warmup=5):
+    """Mean seconds per call over `steps` calls (CUDA events), then one event-bracketed pass for the per-kernel split
+    (left in LAST_KERNELS for report())."""
+    import halide_b200.lib as hlib
     sets = make_sets()
     for i in range(warmup):
         call(*sets[i % len(sets)])
@@ -39,7 +45,18 @@ def time_gpu(make_sets, call, steps, warmup=5):
         call(*sets[i % len(sets)])
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / steps * 1e-3
+    dt = e0.elapsed_time(e1) / steps * 1e-3
+    hlib.profile(True)
+    hlib.profile_reset()
+    reps = 3
+    for i in range(reps):
+        call(*sets[i % len(sets)])
+    torch.cuda.synchronize()
+    rep = hlib.profile_report()
+    hlib.profile(False)
+    LAST_KERNELS.clear()
+    LAST_KERNELS.update({k: {"launches": c / reps, "us": ms / reps * 1e3} for k, (c, ms) in rep.items()})
+    return dt
 
 
 def main():
@@ -54,7 +71,8 @@ def main():
     def report(name, workload, px, alg_bytes, t_gpu, t_cpu, cpu_sample, bound="hbm", flops=None, note=""):
         line = {"pipeline": name, "workload": workload, "us_per_call": t_gpu * 1e6, "Mpixels_per_s": px / 1e6 / t_gpu,
                 "algorithmic_bytes": alg_bytes, "achieved_GBps": alg_bytes / t_gpu / 1e9, "hbm_frac_of_measured": alg_bytes / t_gpu / 1e9 / pk,
-                "bound": bound, "cpu_oracle_ms": t_cpu * 1e3, "cpu_sample": cpu_sample, "cpu_threads": pyoracle.num_threads(), "note": note}
+                "bound": bound, "cpu_oracle_ms": t_cpu * 1e3, "cpu_sample": cpu_sample, "cpu_threads": pyoracle.num_threads(), "note": note,
+                "kernels": dict(LAST_KERNELS)}
         if flops:
             line["achieved_TFLOPs"] = flops / t_gpu / 1e12
         rows.append(line)
