@@ -284,8 +284,10 @@ def run_ours(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
     e0.record()
+    t_host0 = time.perf_counter()
     for i in range(args.steps):
         step(i)
+    host_enqueue_ms = (time.perf_counter() - t_host0) / args.steps * 1e3   # host time to issue one step (async): must stay below ms_per_step
     e1.record()
     barrier()
     sampler.stop()
@@ -447,7 +449,7 @@ def run_ours(args, rank, world, local_rank):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32 internal, u16 I/O", "data": "synthetic",
             "config": cfg, "e2e": e2e,
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
-            "kernels": kernels, "comm": comm,
+            "kernels": kernels, "comm": comm, "host_enqueue_ms_per_step": host_enqueue_ms,
             "l2_detail": f"rotating {NSETS} device-resident frame pair(s) per GPU ({NSETS * 2 * nbytes / 1e6:.0f} MB) > 126 MB L2",
             "extra": {"smooth_frame_Mpixels_per_s": smooth_value,
                       "note": "same call on a low-frequency synthetic frame (coherent LUT / plane gathers); context only"}}

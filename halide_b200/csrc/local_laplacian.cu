@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -200,18 +201,36 @@ int alloc_levels(Plan &p, hb::Scratch &scratch) {
 const dim3 kBlk(32, 8);
 dim3 grid_for(int w, int h) { return dim3((w + 31) / 32, (h + 7) / 8); }
 
-// Resident block slots of a kernel on the current device (per device: a process may drive several).
+// Resident block slots of a kernel on the current device.  The driver queries behind it (function attribute,
+// occupancy) cost several microseconds each — at eight ranks a whole frame is ~0.8 ms of GPU time and ~17 launches — so
+// the answer is cached per (kernel, device, shared-memory size); a process may drive several devices.
+struct SlotKey {
+    const void *kern;
+    int dev;
+    size_t smem;
+    bool operator<(const SlotKey &o) const {
+        return kern != o.kern ? kern < o.kern : (dev != o.dev ? dev < o.dev : smem < o.smem);
+    }
+};
+std::mutex g_slots_mu;
+std::map<SlotKey, int> g_slots;
+
 template<typename Kern>
 int resident_slots(Kern kern, int threads, size_t smem) {
-    int dev = 0, sms = 148, per_sm = 0;
+    int dev = 0;
     cudaGetDevice(&dev);
+    const SlotKey key = {(const void *)kern, dev, smem};
+    std::lock_guard<std::mutex> lock(g_slots_mu);
+    auto it = g_slots.find(key);
+    if (it != g_slots.end()) return it->second;
+    int sms = 148, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) {
         cudaGetLastError();
         per_sm = 1;
     }
-    return sms * per_sm;
+    return g_slots[key] = sms * per_sm;
 }
 
 template<bool BETA1>
@@ -308,7 +327,7 @@ void launch_final(Plan &p, cudaStream_t s) {
         }
         auto launch = [&](auto kern, bool tma_on) {
             const int smem = up2_smem_bytes(true, tma_on);
-            if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  // (per device, cheap)
+            (void)resident_slots(kern, 256, smem);  // (sets the > 48 KB shared-memory attribute once per kernel and device)
             HB_LAUNCH("ll_final2", kern, g, 256, smem, s, p.f, lb[1], lb[1], in_map);
         };
         if (use_tma && beta1) launch(ll_up2_kernel<true, true, true, true>, true);
@@ -324,19 +343,23 @@ void launch_final(Plan &p, cudaStream_t s) {
 
 // Coarse tail in one cooperative launch: levels j0+1 .. J-1 down and up (see ll_coarse_fused_kernel).
 bool launch_coarse_fused(Plan &p, int j0, cudaStream_t s) {
-    int dev = 0, sms = 0, coop = 0, per_sm = 0;
+    int dev = 0, coop = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    static std::map<int, int> coop_ok;  // per device (guarded by g_slots_mu)
+    {
+        std::lock_guard<std::mutex> lock(g_slots_mu);
+        auto it = coop_ok.find(dev);
+        if (it == coop_ok.end()) {
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+            coop_ok[dev] = coop;
+        } else {
+            coop = it->second;
+        }
+    }
+    const int slots = resident_slots(ll_coarse_fused_kernel, 256, 0);  // sms * blocks per SM
+    int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ll_coarse_fused_kernel, 256, 0);
-    // one or two blocks per SM (HALIDE_B200_LL_COOP_BLOCKS_PER_SM): fewer blocks make the grid barriers cheaper, more
-    // threads shorten the phases between them
-    static const int want_per_sm = [] {
-        const char *e = getenv("HALIDE_B200_LL_COOP_BLOCKS_PER_SM");
-        const int v = e ? atoi(e) : 2;
-        return v < 1 ? 1 : (v > 4 ? 4 : v);
-    }();
-    const int max_blocks = coop ? sms * (per_sm > want_per_sm ? want_per_sm : per_sm) : 0;
+    const int max_blocks = coop ? (slots > 2 * sms ? 2 * sms : slots) : 0;
     if (max_blocks <= 0) return false;
     int J = p.J, K = p.K, levels = p.f.levels;
     float flm1 = p.f.flm1;
