@@ -23,6 +23,7 @@ int fail(int code, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
 // ---- stream / launch accounting --------------------------------------------------------------
 cudaStream_t stream();
 void count_launch(const char *name, cudaStream_t s);
+void profile_begin(const char *name, cudaStream_t s);  // event bracket only (closed by after_launch), not counted as a launch
 void after_launch(cudaStream_t s);
 int check_cuda(cudaError_t e, const char *what, int code);
 

@@ -470,6 +470,12 @@ int check_cuda(cudaError_t e, const char *what, int code) {
 
 void count_launch(const char *name, cudaStream_t s) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    profile_begin(name, s);
+}
+
+// The event bracket alone (for stream work that is not one of this library's kernels, e.g. an NCCL group): shows up in the
+// per-kernel profile, not in halide_b200_kernel_launch_count.
+void profile_begin(const char *name, cudaStream_t s) {
     if (g_prof_on.load(std::memory_order_relaxed)) {
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0);

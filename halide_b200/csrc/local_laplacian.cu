@@ -430,13 +430,24 @@ int run_local_laplacian(halide_buffer_t *input, int levels, float alpha, float b
 // Depends only on the whole frame's geometry and the rank count, so every rank computes the same value.
 int choose_coarse_level(const ll::Geom &whole, int nranks, int J, int K) {
     if (g_shard_coarse_level > 0) return g_shard_coarse_level < 2 ? 2 : (g_shard_coarse_level > J - 1 ? J - 1 : g_shard_coarse_level);
-    for (int j = 2; j < J - 1; j++) {
-        const unsigned long long rows = (unsigned long long)(whole.lv[j].sy.n() + nranks - 1) / nranks;
-        // what one rank sends to each peer: its rows of gPyramid[j] + inGPyramid[j]; <= 1.25 MiB keeps the all-to-all a few
-        // tens of microseconds over NVLink while the halo recompute of the finer levels stays ~1 % of a band
-        if (rows * whole.lv[j].gpitch * (K + 1) * sizeof(float) <= (5ull << 18)) return j;
+    // The gathered level trades the two messages of a call against each other: gathering a finer level means a bigger
+    // all-to-all (a rank receives (N-1)/N of the level: gPyramid + inGPyramid, (K + 1) floats per pixel) but a smaller
+    // input halo (about 3 * 2^j frame rows of three uint16 channels per rank, which also is the recomputed work).  Pick the
+    // level with the fewest bytes received per rank; ties go to the finer level (less recompute).  Measured on 4 x B200,
+    // 16K frame: level 6 cost 65 + 55 us of NCCL time per frame, the 18.6 MB input halo alone being bandwidth-bound.
+    const double frame_row_bytes = (double)whole.lv[0].sx.n() * 3 * sizeof(uint16_t);
+    int best = J - 1;
+    double best_bytes = 1e300;
+    for (int j = 2; j < J; j++) {
+        const double halo = 3.0 * (double)(1 << j) * frame_row_bytes;
+        const double level = (double)whole.lv[j].sy.n() * whole.lv[j].gpitch * (K + 1) * sizeof(float);
+        const double bytes = halo + level * (nranks - 1) / (nranks > 0 ? nranks : 1);
+        if (bytes < best_bytes) {
+            best_bytes = bytes;
+            best = j;
+        }
     }
-    return J - 1;
+    return best;
 }
 
 // ---- row-sharded variant (one process per GPU) -----------------------------------------------------------
@@ -580,7 +591,12 @@ int run_local_laplacian_sharded(halide_buffer_t *input, int levels, float alpha,
             if (dn_need) msgs[n++] = {send_dn, (size_t)C * dn_need * rowb, rank + 1, true};
             if (ht) msgs[n++] = {halo_top, (size_t)C * ht * rowb, rank - 1, false};
             if (hbn) msgs[n++] = {halo_bot, (size_t)C * hbn * rowb, rank + 1, false};
-            if (n && (r = hbdist::exchange(msgs, n, s))) return r;
+            if (n) {
+                hb::profile_begin("nccl_input_halo", s);  // (event-bracketed in profile mode like a kernel launch; not counted as one)
+                r = hbdist::exchange(msgs, n, s);
+                hb::after_launch(s);
+                if (r) return r;
+            }
         }
         LevelBuf *lb = p.ls.lv;
         for (int j = 1; j <= jr; j++) launch_down(p, j, s);  // (level jr: only the rows this rank owns)
@@ -601,7 +617,12 @@ int run_local_laplacian_sharded(halide_buffer_t *input, int levels, float alpha,
                 rows_msg(sl[jr].own, q, true);
                 rows_msg(own_q[jr], q, false);
             }
-            if (!msgs.empty() && (r = hbdist::exchange(msgs.data(), (int)msgs.size(), s))) return r;
+            if (!msgs.empty()) {
+                hb::profile_begin("nccl_level_gather", s);
+                r = hbdist::exchange(msgs.data(), (int)msgs.size(), s);
+                hb::after_launch(s);
+                if (r) return r;
+            }
         }
         lb[jr].cy = lb[jr].sy;   // from here on level jr is complete (its pair plane is not: the up-sweep gathers from gp)
         lb[jr].has_pair = 0;

@@ -93,17 +93,25 @@ def test_gloo_world2_control_plane(tmp_path):
 
 
 def test_coarse_level_choice(hb):
-    """The gathered level depends only on the frame and the rank count (every rank must pick the same one): the first
-    level whose per-rank rows are at most 1.25 MiB; the override forces a level."""
+    """The gathered level depends only on the frame and the rank count (every rank must pick the same one): the level
+    that minimises the bytes a rank receives per call — input halo (~3 * 2^j frame rows) plus (N-1)/N of the level; the
+    override forces a level."""
     lvl = hb.capi.halide_b200_ll_shard_plan_level
+    assert lvl(16384, 16384, 8) == 5 and lvl(16384, 16384, 4) == 5 and lvl(16384, 16384, 2) == 5
     assert lvl(3840, 2160 * 2, 2) == 4
-    assert lvl(3840, 2160 * 4, 4) == 4
-    assert lvl(3840, 2160 * 8, 8) == 4
-    assert lvl(16384, 16384, 8) == 5
-    assert lvl(16384, 16384, 2) == 6
-    assert lvl(1000, 1280, 2) == 3
-    hb.capi.halide_b200_ll_shard_coarse_level(5)
-    assert lvl(3840, 2160 * 2, 2) == 5
+    assert lvl(3840, 2160 * 8, 8) == 5
+    assert lvl(1000, 1280, 2) == 4
+
+    def received(w, h, n, j):   # the cost model itself, restated: halo + share of the level, in bytes
+        halo = 3 * (1 << j) * w * 6
+        level = (h // (1 << j) + 3) * (w // (1 << j) + 3) * 9 * 4
+        return halo + level * (n - 1) / n
+    for (w, h, n) in [(16384, 16384, 8), (3840, 4320, 2), (7680, 4320, 4)]:
+        j = lvl(w, h, n)
+        assert 2 <= j <= 7
+        assert received(w, h, n, j) <= 1.1 * min(received(w, h, n, k) for k in range(2, 8))
+    hb.capi.halide_b200_ll_shard_coarse_level(6)
+    assert lvl(3840, 2160 * 2, 2) == 6
     hb.capi.halide_b200_ll_shard_coarse_level(0)
 
 
