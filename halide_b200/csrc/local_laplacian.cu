@@ -572,19 +572,38 @@ int run_local_laplacian_sharded(halide_buffer_t *input, int levels, float alpha,
     if ((r = get_lut(p, s))) return r;
     {
         hb::CallTimer timer(s);
-        // pack my boundary rows per channel ([c][row][w], the layout of the receiver's halo arrays) and exchange
+        // pack my boundary rows per channel ([c][row][w], the layout of the receiver's halo arrays) and exchange — on a
+        // second stream, so that the level-1 kernel's interior rows (every source row inside the band) run meanwhile;
+        // only the few level-1 rows at the band's edges wait for the halo (HALIDE_B200_SHARD_OVERLAP=0: one stream)
+        static const bool overlap = [] {
+            const char *e = getenv("HALIDE_B200_SHARD_OVERLAP");
+            return !(e && e[0] == '0');
+        }();
+        static thread_local cudaStream_t comm_stream = nullptr;
+        static thread_local cudaEvent_t ev_in = nullptr, ev_halo = nullptr;
+        if (overlap && !comm_stream) {
+            cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking);
+            cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&ev_halo, cudaEventDisableTiming);
+        }
+        bool exchanged_async = false;
         {
+            cudaStream_t xs = overlap ? comm_stream : s;
+            if (overlap) {  // the input (and the previous call's use of the scratch blocks) is ordered on s
+                cudaEventRecord(ev_in, s);
+                cudaStreamWaitEvent(xs, ev_in, 0);
+            }
             hbdist::Msg msgs[4];
             int n = 0;
             for (int c = 0; c < C; c++) {
                 const uint16_t *plane = (const uint16_t *)din + (int64_t)c * p.f.in_sc;
                 if (up_need) {
                     cudaMemcpy2DAsync(send_up + (size_t)c * up_need * p.f.in_w, rowb, plane, (size_t)p.f.in_sy * sizeof(uint16_t), rowb,
-                                      up_need, cudaMemcpyDeviceToDevice, s);
+                                      up_need, cudaMemcpyDeviceToDevice, xs);
                 }
                 if (dn_need) {
                     cudaMemcpy2DAsync(send_dn + (size_t)c * dn_need * p.f.in_w, rowb, plane + (int64_t)(p.f.in_h - dn_need) * p.f.in_sy,
-                                      (size_t)p.f.in_sy * sizeof(uint16_t), rowb, dn_need, cudaMemcpyDeviceToDevice, s);
+                                      (size_t)p.f.in_sy * sizeof(uint16_t), rowb, dn_need, cudaMemcpyDeviceToDevice, xs);
                 }
             }
             if (up_need) msgs[n++] = {send_up, (size_t)C * up_need * rowb, rank - 1, true};
@@ -592,14 +611,48 @@ int run_local_laplacian_sharded(halide_buffer_t *input, int levels, float alpha,
             if (ht) msgs[n++] = {halo_top, (size_t)C * ht * rowb, rank - 1, false};
             if (hbn) msgs[n++] = {halo_bot, (size_t)C * hbn * rowb, rank + 1, false};
             if (n) {
-                hb::profile_begin("nccl_input_halo", s);  // (event-bracketed in profile mode like a kernel launch; not counted as one)
-                r = hbdist::exchange(msgs, n, s);
-                hb::after_launch(s);
+                hb::profile_begin("nccl_input_halo", xs);  // (event-bracketed in profile mode like a kernel launch; not counted as one)
+                r = hbdist::exchange(msgs, n, xs);
+                hb::after_launch(xs);
                 if (r) return r;
+                if (overlap) {
+                    cudaEventRecord(ev_halo, xs);
+                    exchanged_async = true;
+                }
             }
         }
         LevelBuf *lb = p.ls.lv;
-        for (int j = 1; j <= jr; j++) launch_down(p, j, s);  // (level jr: only the rows this rank owns)
+        if (exchanged_async && p.K == 8 && !(g_force_naive & 1)) {
+            // level 1 in up to three launches: interior rows (taps 2y-1 .. 2y+2 all inside the band) now, edge rows after the halo
+            const Span cy = lb[1].cy;
+            int i_lo = (p.f.in_y0 + 2) >> 1;                    // smallest y with 2y-1 >= in_y0
+            int i_hi = (p.f.in_y0 + p.f.in_h - 3) >> 1;          // largest y with 2y+2 <= in_y0 + in_h - 1
+            if (i_lo < cy.lo) i_lo = cy.lo;
+            if (i_hi > cy.hi) i_hi = cy.hi;
+            if (i_lo <= i_hi) {
+                lb[1].cy = {i_lo, i_hi};
+                launch_down(p, 1, s);
+            }
+            cudaStreamWaitEvent(s, ev_halo, 0);
+            if (i_lo > i_hi) {  // (band too thin to have interior rows)
+                lb[1].cy = cy;
+                launch_down(p, 1, s);
+            } else {
+                if (cy.lo < i_lo) {
+                    lb[1].cy = {cy.lo, i_lo - 1};
+                    launch_down(p, 1, s);
+                }
+                if (i_hi < cy.hi) {
+                    lb[1].cy = {i_hi + 1, cy.hi};
+                    launch_down(p, 1, s);
+                }
+            }
+            lb[1].cy = cy;
+        } else {
+            if (exchanged_async) cudaStreamWaitEvent(s, ev_halo, 0);
+            launch_down(p, 1, s);
+        }
+        for (int j = 2; j <= jr; j++) launch_down(p, j, s);  // (level jr: only the rows this rank owns)
         // ---- gather level jr: my rows to every rank, every rank's rows into my whole-frame copy ----
         {
             std::vector<hbdist::Msg> msgs;
