@@ -20,7 +20,8 @@ namespace {
 constexpr int kPxPerLane = 8;
 constexpr int kStripW = 32 * kPxPerLane;  // 256 output pixels per warp per row
 constexpr int kWarpsPerBlock = 4;
-int g_force_general = 0;  // test hook (halide_b200_blur_force_general): route aligned frames through the general kernel too
+int g_force_general = 0;  // test hook (halide_b200_blur_force_general): 1 = route aligned frames through the general kernel too,
+                          // >= 8 = aligned kernel with this strip height (small test frames then reach its unclamped main loop)
 
 struct BlurArgs {
     const uint16_t *in;   // element (in_x0, in_y0) of the input == the one feeding output (0,0)
@@ -148,11 +149,16 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) blur3x3_u16_kernel(BlurAr
 // ---- fast path: frames whose rows keep pixel pairs 4-byte aligned (even strides, aligned bases) ----------------------
 // The kernel above pays for arbitrary row misalignment with funnel shifts and selects and is bound by the integer
 // pipe, not by HBM (ALU 63 %, issue 66 %, DRAM 20 % at 8K: profiles/r02_other_pipelines_ncu.md).  When every row starts
-// on an even element — the harness and RunGen frames do: dense rows of W + 2 with W even — a lane can own one aligned
-// PAIR of pixels: two 32-bit loads per row (its own pair and the next one, which hits L1), no shuffles, ~14 integer
-// instructions per pixel.  One warp = a 64-pixel-wide strip walked top to bottom with the last two blur_x rows in
-// registers and kPairAhead input rows in flight per lane.
-constexpr int kPairRows = 32, kPairAhead = 6;
+// on an even element — the harness and RunGen frames do: dense rows of W + 2 with W even — a lane can own two aligned
+// pixel PAIRS (4 pixels): two 32-bit loads per row, the pair to its right from the next lane by shuffle (lane 31 loads
+// it), and all arithmetic in "high-half form" (a u16 value v held as v << 16): 32-bit adds of such values wrap mod 2^16
+// by themselves, umulhi(s, 0x55555556) leaves floor(v / 3) in the upper half (the lower half is (v mod 3) * 2^16 / 3
+// plus an error below 1, which never carries), and one PRMT packs two results.  ~10 integer instructions per pixel.
+// One warp = a 128-pixel-wide strip walked top to bottom with the last two blur_x rows in registers and kQuadAhead
+// input rows in flight per lane; the strip height is chosen on the host so that the strips fill the resident warps of
+// the device a whole number of times (no tail wave).
+constexpr int kQuadAhead = 6, kQuadWarps = 4, kQuadW = 128;
+constexpr uint32_t kThird = 0x55555556u;
 
 __device__ __forceinline__ uint32_t ld_pair(const BlurArgs &a, int64_t off) {  // off even: one aligned word, or guarded halves
     if (off >= a.in_lo && off + 1 <= a.in_hi) return __ldg(reinterpret_cast<const uint32_t *>(a.in + off));
@@ -160,57 +166,125 @@ __device__ __forceinline__ uint32_t ld_pair(const BlurArgs &a, int64_t off) {  /
     uint32_t hi = (off + 1 >= a.in_lo && off + 1 <= a.in_hi) ? a.in[off + 1] : 0u;
     return lo | (hi << 16);
 }
-// blur_x of the lane's two pixels from the words (a0,a1), (a2,a3): every sum wraps mod 2^16 like Halide's u16 adds
-__device__ __forceinline__ void blur_x_pair(uint32_t w, uint32_t wn, uint32_t &b0, uint32_t &b1) {
-    const uint32_t a0 = w & 0xffffu, a1 = w >> 16, a2 = wn & 0xffffu, a3 = wn >> 16;
-    const uint32_t t = a1 + a2;
-    b0 = __umulhi((a0 + t) & 0xffffu, 0x55555556u);  // floor(x / 3), exact for every 32-bit x
-    b1 = __umulhi((t + a3) & 0xffffu, 0x55555556u);
+
+struct QuadRow {
+    uint32_t w0, w1, w2;  // pixels (x, x+1), (x+2, x+3), (x+4, x+5); w2 is the next lane's w0 again (an L1 hit, no shuffle)
+};
+template<bool GUARD>
+__device__ __forceinline__ QuadRow ld_quad(const BlurArgs &a, const uint16_t *row) {  // row = &in(x, y) of this lane
+    QuadRow q;
+    if (!GUARD) {
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(row);
+        q.w0 = __ldg(p);
+        q.w1 = __ldg(p + 1);
+        q.w2 = __ldg(p + 2);
+    } else {
+        const int64_t off = row - a.in;
+        q.w0 = ld_pair(a, off);
+        q.w1 = ld_pair(a, off + 2);
+        q.w2 = ld_pair(a, off + 4);
+    }
+    return q;
+}
+// blur_x of the lane's four pixels, results in high-half form with a clean lower half
+__device__ __forceinline__ void blur_x_quad(const QuadRow &q, uint32_t (&b)[4]) {
+    const uint32_t a0 = q.w0 << 16, a1 = q.w0 & 0xffff0000u, a2 = q.w1 << 16, a3 = q.w1 & 0xffff0000u;
+    const uint32_t a4 = q.w2 << 16, a5 = q.w2 & 0xffff0000u;
+    b[0] = __umulhi(a0 + a1 + a2, kThird) & 0xffff0000u;
+    b[1] = __umulhi(a1 + a2 + a3, kThird) & 0xffff0000u;
+    b[2] = __umulhi(a2 + a3 + a4, kThird) & 0xffff0000u;
+    b[3] = __umulhi(a3 + a4 + a5, kThird) & 0xffff0000u;
 }
 
-__global__ void __launch_bounds__(128) blur3x3_u16_pair_kernel(BlurArgs a) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x0 = (blockIdx.x * 4 + warp) * 64 + 2 * lane;
-    const int y0 = blockIdx.y * kPairRows;
-    if (x0 >= a.w || y0 >= a.h) return;
-    const int y1 = min(y0 + kPairRows, a.h);
-    const int last_in = y1 + 1;  // last input row read
-    uint32_t qw[kPairAhead], qn[kPairAhead];  // input rows in flight (row y + 2 + k at the top of iteration y)
-    uint32_t r0a, r0b, r1a, r1b;
-    {
-        const int64_t o0 = (int64_t)y0 * a.in_stride_y + x0, o1 = o0 + a.in_stride_y;
-        const uint32_t w0 = ld_pair(a, o0), n0 = ld_pair(a, o0 + 2), w1 = ld_pair(a, o1), n1 = ld_pair(a, o1 + 2);
-#pragma unroll
-        for (int k = 0; k < kPairAhead; k++) {
-            const int yy = min(y0 + 2 + k, last_in);
-            const int64_t o = (int64_t)yy * a.in_stride_y + x0;
-            qw[k] = ld_pair(a, o);
-            qn[k] = ld_pair(a, o + 2);
+// Walks one strip.  `rin` is the row pointer of the next input row to request, `rout` the output row pointer.  The
+// bulk of the strip runs without any test per row; only the refills of the last rows (which would run past the
+// strip's last input row) use the clamped request, which re-requests a valid row.
+template<bool GUARD>
+struct QuadStrip {
+    const BlurArgs &a;
+    const uint16_t *rin;
+    uint16_t *rout;
+    int next_row, last_in, x;
+    QuadRow q[kQuadAhead];
+    uint32_t r0[4], r1[4];
+
+    template<bool CLAMP>
+    __device__ __forceinline__ QuadRow fetch() {
+        const QuadRow t = ld_quad<GUARD>(a, rin);
+        if (!CLAMP) {
+            rin += a.in_stride_y;
+        } else if (next_row < last_in) {
+            next_row++;
+            rin += a.in_stride_y;
         }
-        blur_x_pair(w0, n0, r0a, r0b);
-        blur_x_pair(w1, n1, r1a, r1b);
+        return t;
     }
-    const bool both = x0 + 1 < a.w;
-    for (int yb = y0; yb < y1; yb += kPairAhead) {
+    template<bool CLAMP>
+    __device__ __forceinline__ void row(int k) {
+        uint32_t r2[4];
+        blur_x_quad(q[k], r2);
+        q[k] = fetch<CLAMP>();
+        uint32_t o[4];
 #pragma unroll
-        for (int k = 0; k < kPairAhead; k++) {
-            const int y = yb + k;
-            if (y < y1) {
-                uint32_t r2a, r2b;
-                blur_x_pair(qw[k], qn[k], r2a, r2b);
-                const int yy = min(y + 2 + kPairAhead, last_in);  // refill this slot (rows past the strip: a valid row again)
-                const int64_t o = (int64_t)yy * a.in_stride_y + x0;
-                qw[k] = ld_pair(a, o);
-                qn[k] = ld_pair(a, o + 2);
-                const uint32_t oa = __umulhi((r0a + r1a + r2a) & 0xffffu, 0x55555556u);
-                const uint32_t ob = __umulhi((r0b + r1b + r2b) & 0xffffu, 0x55555556u);
-                uint16_t *dst = a.out + (int64_t)y * a.out_stride_y + x0;
-                if (both) *reinterpret_cast<uint32_t *>(dst) = oa | (ob << 16);
-                else *dst = (uint16_t)oa;
-                r0a = r1a; r0b = r1b;
-                r1a = r2a; r1b = r2b;
+        for (int i = 0; i < 4; i++) o[i] = __umulhi(r0[i] + r1[i] + r2[i], kThird);
+        const uint32_t p0 = __byte_perm(o[0], o[1], 0x7632), p1 = __byte_perm(o[2], o[3], 0x7632);
+        if (!GUARD) {
+            reinterpret_cast<uint32_t *>(rout)[0] = p0;
+            reinterpret_cast<uint32_t *>(rout)[1] = p1;
+        } else {
+            if (x + 1 < a.w) reinterpret_cast<uint32_t *>(rout)[0] = p0;
+            else if (x < a.w) rout[0] = (uint16_t)(p0 & 0xffffu);
+            if (x + 3 < a.w) reinterpret_cast<uint32_t *>(rout)[1] = p1;
+            else if (x + 2 < a.w) rout[2] = (uint16_t)(p1 & 0xffffu);
+        }
+        rout += a.out_stride_y;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { r0[i] = r1[i]; r1[i] = r2[i]; }
+    }
+    __device__ __forceinline__ void run(int y0, int y1) {
+        last_in = y1 + 1;  // last input row read; y0 + 2 <= last_in
+        rin = a.in + ((int64_t)y0 * a.in_stride_y + x);
+        rout = a.out + ((int64_t)y0 * a.out_stride_y + x);
+        const QuadRow t0 = fetch<false>(), t1 = fetch<false>();
+        next_row = y0 + 2;
+#pragma unroll
+        for (int k = 0; k < kQuadAhead; k++) q[k] = fetch<true>();
+        blur_x_quad(t0, r0);
+        blur_x_quad(t1, r1);
+        int y = y0;
+        // the refill of row y asks for input row y + 2 + kQuadAhead and then steps once more: unclamped while even that
+        // step stays <= last_in for a whole group
+        for (; y + 2 * kQuadAhead < y1; y += kQuadAhead) {
+#pragma unroll
+            for (int k = 0; k < kQuadAhead; k++) row<false>(k);
+        }
+        next_row = min(y + 2 + kQuadAhead, last_in);  // rin points at that row already
+        for (; y < y1; y += kQuadAhead) {
+#pragma unroll
+            for (int k = 0; k < kQuadAhead; k++) {
+                if (y + k < y1) row<true>(k);  // warp-uniform
             }
         }
+    }
+};
+
+// a.rows_per_warp = strip height; strips are numbered x-fastest so the warps of a block read adjacent spans of a row
+__global__ void __launch_bounds__(32 * kQuadWarps) blur3x3_u16_quad_kernel(BlurArgs a, int strips_x, int strips) {
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * kQuadWarps + (threadIdx.x >> 5);
+    if (t >= strips) return;
+    const int sx = t % strips_x, sy = t / strips_x;
+    const int xw = sx * kQuadW, y0 = sy * a.rows_per_warp;
+    const int y1 = min(y0 + a.rows_per_warp, a.h);
+    // whole strip (and the two input columns to its right) inside the output width: nothing to guard
+    if (xw + kQuadW <= a.w) {
+        QuadStrip<false> st{a};
+        st.x = xw + 4 * lane;
+        st.run(y0, y1);
+    } else {
+        QuadStrip<true> st{a};
+        st.x = xw + 4 * lane;
+        st.run(y0, y1);
     }
 }
 
@@ -283,13 +357,37 @@ extern "C" int halide_blur(halide_buffer_t *input, halide_buffer_t *blur_y) {
 
     // pixel pairs 4-byte aligned on every row of both buffers -> the pair kernel; anything else -> the general kernel
     const bool pair_ok = ((reinterpret_cast<uintptr_t>(a.in) | reinterpret_cast<uintptr_t>(a.out)) & 3) == 0 &&
-                         (a.in_stride_y & 1) == 0 && (a.out_stride_y & 1) == 0 && !g_force_general;
+                         (a.in_stride_y & 1) == 0 && (a.out_stride_y & 1) == 0 && g_force_general != 1;
     cudaStream_t s = hb::stream();
     {
         hb::CallTimer timer(s);
         if (pair_ok) {
-            dim3 gp((w + 255) / 256, (h + kPairRows - 1) / kPairRows);
-            HB_LAUNCH("blur3x3_u16_pair", blur3x3_u16_pair_kernel, gp, 128, 0, s, a);
+            // strips of 128 columns; height such that the strips fill the resident warps a whole number of times
+            static int resident = 0;  // blocks per SM x SMs (per process: one device per process)
+            if (!resident) {
+                int per_sm = 0, dev = 0, sms = 0;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blur3x3_u16_quad_kernel, 32 * kQuadWarps, 0);
+                resident = (per_sm > 0 ? per_sm : 8) * (sms > 0 ? sms : 148);
+            }
+            const int sxq = (w + kQuadW - 1) / kQuadW;
+            const int64_t slots = (int64_t)resident * kQuadWarps;
+            int qrows = 8;
+            for (int m = 1; m <= 64; m++) {
+                const int64_t sy = m * slots / sxq;
+                if (sy < 1) continue;
+                const int rr = (int)((h + sy - 1) / sy);
+                if (rr <= 64 || m == 64) {
+                    qrows = rr < 8 ? 8 : rr;
+                    break;
+                }
+            }
+            if (g_force_general >= 8) qrows = g_force_general;
+            a.rows_per_warp = qrows;
+            const int strips_q = sxq * ((h + qrows - 1) / qrows);
+            HB_LAUNCH("blur3x3_u16_quad", blur3x3_u16_quad_kernel, (strips_q + kQuadWarps - 1) / kQuadWarps, 32 * kQuadWarps, 0, s, a,
+                      sxq, strips_q);
         } else {
             HB_LAUNCH("blur3x3_u16", blur3x3_u16_kernel, grid, 32 * kWarpsPerBlock, 0, s, a);
         }
@@ -299,7 +397,8 @@ extern "C" int halide_blur(halide_buffer_t *input, halide_buffer_t *blur_y) {
     return 0;
 }
 
-// Test hook: 1 = always take the general (any alignment) kernel, so both kernels stay covered by the parity tests.
+// Test hook: 1 = always take the general (any alignment) kernel, so both kernels stay covered by the parity tests;
+// >= 8 = the aligned kernel with strips of that many rows.
 extern "C" void halide_b200_blur_force_general(int enable) {
     g_force_general = enable;
 }

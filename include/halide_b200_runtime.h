@@ -297,7 +297,8 @@ int halide_b200_ll_shard_plan_level(int32_t frame_w, int32_t frame_h, int32_t nr
  * 8 no fused coarse launch, 16 general-layout final kernel, 64 no TMA frame tile in the final
  * kernel) so every code path stays covered by the parity tests. */
 void halide_b200_ll_force_generic(int mask);
-/* halide_blur test hook: 1 = route 4-byte-aligned frames through the general (any alignment) kernel as well. */
+/* halide_blur test hook: 1 = route 4-byte-aligned frames through the general (any alignment) kernel as well;
+ * >= 8 = aligned kernel with strips of that many rows (0 restores the defaults). */
 void halide_b200_blur_force_general(int enable);
 /* conv_layer: 1 = tcgen05/TMEM/TMA implicit GEMM (3xTF32 split), 0 = FP32 SIMT kernel (also HALIDE_B200_CONV=tc|simt). */
 void halide_b200_conv_use_tensor_cores(int enable);

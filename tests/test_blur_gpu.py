@@ -75,11 +75,33 @@ def test_blur_device_resident_buffers(hb, oracle):
     assert np.array_equal(got, oracle.blur(inp))
 
 
+def test_blur_8k_full_frame_matches_oracle(hb, oracle):
+    """The bench_all frame (7680x4320 output): full compare against the oracle (tens of ms on the CPU).  At this size the
+    aligned kernel runs tall strips (its unclamped main loop) on unguarded 128-column strips."""
+    inp = u16_frame((4322, 7682), 77)
+    got = run_blur(hb, inp, (4320, 7680))
+    assert np.array_equal(got, oracle.blur(inp))
+
+
+@pytest.mark.parametrize("rows", [8, 13, 19, 25, 64])
+def test_blur_aligned_kernel_strip_heights(hb, oracle, rows):
+    """Strip heights around the prefetch depth: the row loop has an unclamped main part and a clamped tail; every split
+    of a strip between them must give the same frame (widths: whole strips, a ragged last strip, an odd width)."""
+    l = hb.load_library()
+    try:
+        l.halide_b200_blur_force_general(rows)
+        for h, w in ((100, 256), (67, 300), (90, 131)):
+            inp = u16_frame((h + 2, w + 2 + (w & 1)), rows + w)
+            assert np.array_equal(run_blur(hb, inp, (h, w)), oracle.blur(inp, out_shape=(h, w))), (rows, h, w)
+    finally:
+        l.halide_b200_blur_force_general(0)
+
+
 @pytest.mark.parametrize("h,w", [(64, 128), (37, 190), (130, 257), (200, 1000)])
 def test_blur_pair_and_general_kernels(hb, oracle, h, w):
-    """Frames whose rows keep pixel pairs 4-byte aligned (even row strides) take the aligned-pair kernel; the hook routes
-    the same frame through the general (any alignment) kernel.  Both must equal the oracle; odd output widths and odd
-    column offsets (which fall back to the general kernel by themselves) included."""
+    """Frames whose rows keep pixel pairs 4-byte aligned (even row strides) take the aligned kernel (a lane = two pixel
+    pairs); the hook routes the same frame through the general (any alignment) kernel.  Both must equal the oracle; odd
+    output widths and odd column offsets (which fall back to the general kernel by themselves) included."""
     inp = u16_frame((h + 2, w + 2 + (w & 1)), 100 + w)   # even row stride
     want = oracle.blur(inp, out_shape=(h, w))
     l = hb.load_library()

@@ -61,6 +61,8 @@ def time_gpu(make_sets, call, steps, warmup=5):
 
 def main():
     quick = "--quick" in sys.argv
+    only = sys.argv[sys.argv.index("--only") + 1].split(",") if "--only" in sys.argv else None
+    want = lambda name: only is None or name in only
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev)
     g.manual_seed(7)
@@ -88,74 +90,74 @@ def main():
         return min(t)
 
     nsets = 4
-    # ---- blur, config 1: 1920x1080 u16 (+ an 8K frame so the kernel is not launch-bound)
-    for (W, H) in [(1920, 1080), (7680, 4320)]:
+    if want("blur"):  # ---- blur, config 1: 1920x1080 u16 (+ an 8K frame so the kernel is not launch-bound)
+        for (W, H) in [(1920, 1080), (7680, 4320)]:
+            def mk():
+                return [(HalideBuffer.from_torch(u16((H + 2, W + 2), dev, g)), HalideBuffer.from_torch(torch.zeros((H, W), dtype=torch.uint16, device=dev)))
+                        for _ in range(nsets * (8 if W < 4000 else 1))]
+            t = time_gpu(mk, filters.halide_blur, 200 if W < 4000 else 50)
+            a = np.random.default_rng(0).integers(0, 65536, (H + 2, W + 2), dtype=np.uint16)
+            report("blur", f"{W}x{H} u16", W * H, 4 * W * H, t, cpu_time(lambda: pyoracle.blur(a)), "full frame")
+    if want("bilateral_grid"):  # ---- bilateral_grid, config 3: 7680x4320 f32
+        W, H = (7680, 4320)
         def mk():
-            return [(HalideBuffer.from_torch(u16((H + 2, W + 2), dev, g)), HalideBuffer.from_torch(torch.zeros((H, W), dtype=torch.uint16, device=dev)))
-                    for _ in range(nsets * (8 if W < 4000 else 1))]
-        t = time_gpu(mk, filters.halide_blur, 200 if W < 4000 else 50)
-        a = np.random.default_rng(0).integers(0, 65536, (H + 2, W + 2), dtype=np.uint16)
-        report("blur", f"{W}x{H} u16", W * H, 4 * W * H, t, cpu_time(lambda: pyoracle.blur(a)), "full frame")
-    # ---- bilateral_grid, config 3: 7680x4320 f32
-    W, H = (7680, 4320)
-    def mk():
-        return [(HalideBuffer.from_torch(torch.rand((H, W), dtype=torch.float32, device=dev, generator=g)),
-                 HalideBuffer.from_torch(torch.zeros((H, W), dtype=torch.float32, device=dev))) for _ in range(2)]
-    t = time_gpu(mk, lambda i, o: filters.bilateral_grid(i, 0.1, o), 20)
-    a = np.random.default_rng(0).random((H // 4, W), dtype=np.float32)
-    report("bilateral_grid", f"{W}x{H} f32 r_sigma=0.1", W * H, 8 * W * H, t, cpu_time(lambda: pyoracle.bilateral_grid(a, 0.1)) * 4, "1/4 of the frame x4")
-    # ---- nl_means, config 4 (single GPU here): 3840x2160x3 f32, patch 3 / search 7
-    W, H = (3840, 2160)
-    def mk():
-        return [(HalideBuffer.from_torch(torch.rand((3, H, W), dtype=torch.float32, device=dev, generator=g)),
-                 HalideBuffer.from_torch(torch.zeros((3, H, W), dtype=torch.float32, device=dev))) for _ in range(2)]
-    t = time_gpu(mk, lambda i, o: filters.nl_means(i, 3, 7, 0.12, o), 5 if quick else 10)
-    a = np.random.default_rng(0).random((3, 64, W // 8), dtype=np.float32)
-    scale = (H / 64) * 8
-    report("nl_means", f"{W}x{H}x3 f32 patch 3 search 7", W * H, 24 * W * H, t, cpu_time(lambda: pyoracle.nl_means(a, 3, 7, 0.12), 1) * scale,
-           "480x64 crop scaled by area", bound="fp32", flops=W * H * 49 * (9 * 8 + 30.0))
-    # ---- stencil_chain: harness frame 1536x2560 u16
-    W, H = (1536, 2560)
-    def mk():
-        return [(HalideBuffer.from_torch(u16((H, W), dev, g)), HalideBuffer.from_torch(torch.zeros((H, W), dtype=torch.uint16, device=dev)))
-                for _ in range(nsets)]
-    t = time_gpu(mk, filters.stencil_chain, 20)
-    a = np.random.default_rng(0).integers(0, 65536, (H // 4, W), dtype=np.uint16)
-    report("stencil_chain", f"{W}x{H} u16, 32 stages", W * H, 4 * W * H, t, cpu_time(lambda: pyoracle.stencil_chain(a)) * 4, "1/4 of the frame x4",
-           bound="int-alu", note="800 MAC/px in the reference formulation (320 after the exact separable rewrite)")
-    # ---- camera_pipe: harness frame 2592x1968 raw -> 2560x1920x3
-    W, H = (2560, 1920)
-    m32 = torch.tensor(M3200, dtype=torch.float32, device=dev)
-    m70 = torch.tensor(M7000, dtype=torch.float32, device=dev)
-    b32, b70 = HalideBuffer.from_torch(m32), HalideBuffer.from_torch(m70)
-    def mk():
-        return [(HalideBuffer.from_torch(torch.randint(0, 1024, (H + 48, W + 32), dtype=torch.int16, device=dev, generator=g).view(torch.uint16)),
-                 HalideBuffer.from_torch(torch.zeros((3, H, W), dtype=torch.uint8, device=dev))) for _ in range(nsets * 2)]
-    t = time_gpu(mk, lambda i, o: filters.camera_pipe(i, b32, b70, 3700.0, 2.0, 50.0, 1.0, 25, 1023, o), 50)
-    raw = np.random.default_rng(0).integers(0, 1024, (H + 48, W + 32), dtype=np.uint16)
-    t_cpu = cpu_time(lambda: pyoracle.camera_pipe(raw, np.array(M3200, np.float32), np.array(M7000, np.float32), 3700.0, 2.0, 50.0, 1.0, 25,
-                                                    1023, (3, H, W)))
-    report("camera_pipe", f"{W + 32}x{H + 48} raw -> {W}x{H}x3 u8", W * H, 5 * W * H, t, t_cpu, "full frame")
-    # ---- conv_layer: fixed shapes
-    ti = torch.rand((5, 82, 102, 128), dtype=torch.float32, device=dev, generator=g)
-    tf = torch.rand((128, 3, 3, 128), dtype=torch.float32, device=dev, generator=g)
-    tb = torch.rand((128,), dtype=torch.float32, device=dev, generator=g)
-    bi, bf, bb = (HalideBuffer.from_torch(x) for x in (ti, tf, tb))
-    def mk():
-        return [(HalideBuffer.from_torch(torch.zeros((5, 80, 100, 128), dtype=torch.float32, device=dev)),) for _ in range(2)]
-    t = time_gpu(mk, lambda o: filters.conv_layer(bi, bf, bb, o), 20)
-    ci, cf, cb = ti[:1].cpu().numpy(), tf.cpu().numpy(), tb.cpu().numpy()
-    report("conv_layer", "N5 CI128 CO128 100x80 3x3 f32", 5 * 80 * 100, 42.5e6, t, cpu_time(lambda: pyoracle.conv_layer(ci, cf, cb), 1) * 5,
-           "1 of 5 images x5", bound="tensor (tcgen05 kind::tf32, 3-term split)", flops=11.8e9)
-    # ---- local_laplacian (headline; bench.py measures it with the full contract)
-    for (W, H) in [(3840, 2160), (16384, 2048)] + ([] if quick else [(16384, 16384)]):
+            return [(HalideBuffer.from_torch(torch.rand((H, W), dtype=torch.float32, device=dev, generator=g)),
+                     HalideBuffer.from_torch(torch.zeros((H, W), dtype=torch.float32, device=dev))) for _ in range(2)]
+        t = time_gpu(mk, lambda i, o: filters.bilateral_grid(i, 0.1, o), 20)
+        a = np.random.default_rng(0).random((H // 4, W), dtype=np.float32)
+        report("bilateral_grid", f"{W}x{H} f32 r_sigma=0.1", W * H, 8 * W * H, t, cpu_time(lambda: pyoracle.bilateral_grid(a, 0.1)) * 4, "1/4 of the frame x4")
+    if want("nl_means"):  # ---- nl_means, config 4 (single GPU here): 3840x2160x3 f32, patch 3 / search 7
+        W, H = (3840, 2160)
         def mk():
-            return [(HalideBuffer.from_torch(u16((3, H, W), dev, g)), HalideBuffer.from_torch(torch.zeros((3, H, W), dtype=torch.uint16, device=dev)))
-                    for _ in range(nsets if W * H < 1e8 else 1)]
-        t = time_gpu(mk, lambda i, o: filters.local_laplacian(i, 8, 1.0 / 7.0, 1.0, o), 20 if W * H < 1e8 else 5)
-        a = np.random.default_rng(0).integers(0, 65536, (3, 1080, 3840), dtype=np.uint16)
-        report("local_laplacian", f"{W}x{H}x3 u16 levels 8", W * H, 12 * W * H, t, cpu_time(lambda: pyoracle.local_laplacian(a, 8, 1 / 7, 1.0)) * (W * H / (3840 * 1080)),
-               "3840x1080 band scaled by area")
+            return [(HalideBuffer.from_torch(torch.rand((3, H, W), dtype=torch.float32, device=dev, generator=g)),
+                     HalideBuffer.from_torch(torch.zeros((3, H, W), dtype=torch.float32, device=dev))) for _ in range(2)]
+        t = time_gpu(mk, lambda i, o: filters.nl_means(i, 3, 7, 0.12, o), 5 if quick else 10)
+        a = np.random.default_rng(0).random((3, 64, W // 8), dtype=np.float32)
+        scale = (H / 64) * 8
+        report("nl_means", f"{W}x{H}x3 f32 patch 3 search 7", W * H, 24 * W * H, t, cpu_time(lambda: pyoracle.nl_means(a, 3, 7, 0.12), 1) * scale,
+               "480x64 crop scaled by area", bound="fp32", flops=W * H * 49 * (9 * 8 + 30.0))
+    if want("stencil_chain"):  # ---- stencil_chain: harness frame 1536x2560 u16
+        W, H = (1536, 2560)
+        def mk():
+            return [(HalideBuffer.from_torch(u16((H, W), dev, g)), HalideBuffer.from_torch(torch.zeros((H, W), dtype=torch.uint16, device=dev)))
+                    for _ in range(nsets)]
+        t = time_gpu(mk, filters.stencil_chain, 20)
+        a = np.random.default_rng(0).integers(0, 65536, (H // 4, W), dtype=np.uint16)
+        report("stencil_chain", f"{W}x{H} u16, 32 stages", W * H, 4 * W * H, t, cpu_time(lambda: pyoracle.stencil_chain(a)) * 4, "1/4 of the frame x4",
+               bound="int-alu", note="800 MAC/px in the reference formulation (320 after the exact separable rewrite)")
+    if want("camera_pipe"):  # ---- camera_pipe: harness frame 2592x1968 raw -> 2560x1920x3
+        W, H = (2560, 1920)
+        m32 = torch.tensor(M3200, dtype=torch.float32, device=dev)
+        m70 = torch.tensor(M7000, dtype=torch.float32, device=dev)
+        b32, b70 = HalideBuffer.from_torch(m32), HalideBuffer.from_torch(m70)
+        def mk():
+            return [(HalideBuffer.from_torch(torch.randint(0, 1024, (H + 48, W + 32), dtype=torch.int16, device=dev, generator=g).view(torch.uint16)),
+                     HalideBuffer.from_torch(torch.zeros((3, H, W), dtype=torch.uint8, device=dev))) for _ in range(nsets * 2)]
+        t = time_gpu(mk, lambda i, o: filters.camera_pipe(i, b32, b70, 3700.0, 2.0, 50.0, 1.0, 25, 1023, o), 50)
+        raw = np.random.default_rng(0).integers(0, 1024, (H + 48, W + 32), dtype=np.uint16)
+        t_cpu = cpu_time(lambda: pyoracle.camera_pipe(raw, np.array(M3200, np.float32), np.array(M7000, np.float32), 3700.0, 2.0, 50.0, 1.0, 25,
+                                                        1023, (3, H, W)))
+        report("camera_pipe", f"{W + 32}x{H + 48} raw -> {W}x{H}x3 u8", W * H, 5 * W * H, t, t_cpu, "full frame")
+    if want("conv_layer"):  # ---- conv_layer: fixed shapes
+        ti = torch.rand((5, 82, 102, 128), dtype=torch.float32, device=dev, generator=g)
+        tf = torch.rand((128, 3, 3, 128), dtype=torch.float32, device=dev, generator=g)
+        tb = torch.rand((128,), dtype=torch.float32, device=dev, generator=g)
+        bi, bf, bb = (HalideBuffer.from_torch(x) for x in (ti, tf, tb))
+        def mk():
+            return [(HalideBuffer.from_torch(torch.zeros((5, 80, 100, 128), dtype=torch.float32, device=dev)),) for _ in range(2)]
+        t = time_gpu(mk, lambda o: filters.conv_layer(bi, bf, bb, o), 20)
+        ci, cf, cb = ti[:1].cpu().numpy(), tf.cpu().numpy(), tb.cpu().numpy()
+        report("conv_layer", "N5 CI128 CO128 100x80 3x3 f32", 5 * 80 * 100, 42.5e6, t, cpu_time(lambda: pyoracle.conv_layer(ci, cf, cb), 1) * 5,
+               "1 of 5 images x5", bound="tensor (tcgen05 kind::tf32, 3-term split)", flops=11.8e9)
+    if want("local_laplacian"):  # ---- local_laplacian (headline; bench.py measures it with the full contract)
+        for (W, H) in [(3840, 2160), (16384, 2048)] + ([] if quick else [(16384, 16384)]):
+            def mk():
+                return [(HalideBuffer.from_torch(u16((3, H, W), dev, g)), HalideBuffer.from_torch(torch.zeros((3, H, W), dtype=torch.uint16, device=dev)))
+                        for _ in range(nsets if W * H < 1e8 else 1)]
+            t = time_gpu(mk, lambda i, o: filters.local_laplacian(i, 8, 1.0 / 7.0, 1.0, o), 20 if W * H < 1e8 else 5)
+            a = np.random.default_rng(0).integers(0, 65536, (3, 1080, 3840), dtype=np.uint16)
+            report("local_laplacian", f"{W}x{H}x3 u16 levels 8", W * H, 12 * W * H, t, cpu_time(lambda: pyoracle.local_laplacian(a, 8, 1 / 7, 1.0)) * (W * H / (3840 * 1080)),
+                   "3840x1080 band scaled by area")
     json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "bench_all.json"), "w"), indent=1)
 
 
