@@ -295,7 +295,8 @@ void halide_b200_ll_shard_coarse_level(int level);
 int halide_b200_ll_shard_plan_level(int32_t frame_w, int32_t frame_h, int32_t nranks);
 /* Test hook: bitmask routing levels==8 calls through the generic kernels (1 down, 2 up, 4 final,
  * 8 no fused coarse launch, 16 general-layout final kernel, 64 no TMA frame tile in the final
- * kernel) so every code path stays covered by the parity tests. */
+ * kernel, 256 = the 48-row-tile variant of the TMA final kernel, 128 = its default 32-row tiles) so
+ * every code path stays covered by the parity tests. */
 void halide_b200_ll_force_generic(int mask);
 /* halide_blur test hook: 1 = route 4-byte-aligned frames through the general (any alignment) kernel as well;
  * >= 8 = aligned kernel with strips of that many rows (0 restores the defaults). */

@@ -15,7 +15,7 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("world,w,band_h", [(2, 1000, 640), (2, 333, 517)])
+@pytest.mark.parametrize("world,w,band_h", [(1, 1000, 640), (2, 1000, 640), (2, 333, 517)])  # (world 1: the sharded code path alone)
 def test_sharded_local_laplacian_matches_single_gpu(world, w, band_h):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
