@@ -121,32 +121,38 @@ __global__ void __launch_bounds__(256) bg_blur_xy_kernel(BGParams p, int rows_pe
 }
 
 // ---- K3: trilinear slice + normalise -----------------------------------------------------------------
-// One block = 120 x 8 pixels = one row of grid cells: the 16 x 2 cells (x nz planes x 2 channels) its pixels interpolate
-// between are staged once into shared memory as [z][cell] float2 with 32 cells per plane, so that a corner fetch is one
-// 8-byte shared load whose bank depends on the cell only, never on the data-dependent plane zi.  (The first version
-// gathered the eight corners of every pixel straight from L1: up to 13 cache lines per warp instruction, and the L1
-// data pipe, not HBM, was the bound — 92 % busy, profiles/r02_other_pipelines_ncu.md.)  30 of 32 lanes hold 4 pixels each.
-constexpr int kSliceW = 120, kSliceCells = 16;
+// One block = 128 x 8 pixels = one row of grid cells: the 17 x 2 cells (x nz planes x 2 channels) its pixels interpolate
+// between are staged once into shared memory as [z][cell row][24] float2, so that a corner fetch is one 8-byte shared
+// load.  Lane l of a warp owns the 4 pixels of cell (l & 15) at offset 4 * (l >> 4): the 16 lanes of a half-warp — the
+// unit an 8-byte shared load is served in — then read 16 DIFFERENT cells, and with a plane stride of 48 entries
+// (= 0 mod 16 bank pairs) the bank of a fetch depends on the cell only, never on the data-dependent plane zi: no
+// conflicts whatever the image.  (First version: corners gathered straight from L1, 92 % of the L1 data pipe.  Second:
+// shared memory, but lanes 2c and 2c+1 shared cell c, so on a noisy image — different zi — every fetch was a two-way
+// conflict: 58 % of the wavefronts, L1 data pipe 96 % busy, profiles/r02_other_pipelines_ncu.md.)
+constexpr int kSliceW = 128, kSliceCells = 17, kSlicePitch = 24;
 
 __global__ void __launch_bounds__(256) bg_slice_kernel(BGParams p) {
-    extern __shared__ float2 s_grid[];  // [nz][2 * kSliceCells]
+    extern __shared__ float2 s_grid[];  // [nz][2][kSlicePitch]
     const int lane = threadIdx.x, row = threadIdx.y, tid = row * 32 + lane;
     const int X0 = (p.out_x0 & ~(S - 1)) + blockIdx.x * kSliceW, Y0 = (p.out_y0 & ~(S - 1)) + blockIdx.y * S;
     const int cx0 = (X0 >> 3) - p.gx0, cy0 = (Y0 >> 3) - p.gy0;  // first stored cell of the tile
     {
         const float2 *g = reinterpret_cast<const float2 *>(p.grid_b);
         for (int it = tid; it < 2 * kSliceCells * p.nz; it += 256) {
-            const int z = it % p.nz, cell = it / p.nz;  // (z fastest: the planes of a cell are contiguous in HBM)
-            const int cx = min(cx0 + (cell & (kSliceCells - 1)), p.gw - 1), cy = min(cy0 + (cell >> 4), p.gh - 1);
-            s_grid[z * (2 * kSliceCells) + cell] = __ldg(g + ((size_t)cy * p.gw + cx) * p.nz + z);
+            // (cell fastest: consecutive lanes store to consecutive banks; the planes of a cell are contiguous in HBM, so
+            // the later planes of a cell hit the line the first one brought into L1)
+            const int z = it / (2 * kSliceCells), cell = it - z * (2 * kSliceCells);
+            const int cr = cell >= kSliceCells ? 1 : 0, cc = cell - cr * kSliceCells;
+            const int cx = min(cx0 + cc, p.gw - 1), cy = min(cy0 + cr, p.gh - 1);
+            s_grid[(z * 2 + cr) * kSlicePitch + cc] = __ldg(g + ((size_t)cy * p.gw + cx) * p.nz + z);
         }
     }
     __syncthreads();
-    const int y = Y0 + row, x = X0 + 4 * lane;
-    if (lane >= kSliceW / 4 || y < p.out_y0 || y >= p.out_y0 + p.H || x + 3 < p.out_x0 || x >= p.out_x0 + p.W) return;
+    const int y = Y0 + row, x = X0 + 8 * (lane & 15) + 4 * (lane >> 4);
+    if (y < p.out_y0 || y >= p.out_y0 + p.H || x + 3 < p.out_x0 || x >= p.out_x0 + p.W) return;
     const float *ip = p.in + (int64_t)(y - p.in_y0) * p.in_sy + (x - p.in_x0);
     float *op = p.out + (int64_t)(y - p.out_y0) * p.out_sy + (x - p.out_x0);
-    const float2 *c00 = s_grid + (lane >> 1);  // cell (xi, yi) of this thread's four pixels; xi + 1: +1, yi + 1: +kSliceCells
+    const float2 *c00 = s_grid + (lane & 15);  // cell (xi, yi) of this thread's four pixels; xi + 1: +1, yi + 1: +kSlicePitch
     const float yf = __fmul_rn((float)(y & (S - 1)), 0.125f);
     auto px = [&](float raw, int xx) -> float {
         const float val = hl::clampf(raw, 0.0f, 1.0f);
@@ -155,9 +161,9 @@ __global__ void __launch_bounds__(256) bg_slice_kernel(BGParams p) {
         const float zf = __fsub_rn(zv, (float)zi);
         zi = min(zi, p.nz - 2);
         const float xf = __fmul_rn((float)(xx & (S - 1)), 0.125f);
-        const float2 *c = c00 + zi * (2 * kSliceCells);
-        const float2 a0 = c[0], b0 = c[1], d0 = c[kSliceCells], e0 = c[kSliceCells + 1];
-        const float2 a1 = c[2 * kSliceCells], b1 = c[2 * kSliceCells + 1], d1 = c[3 * kSliceCells], e1 = c[3 * kSliceCells + 1];
+        const float2 *c = c00 + zi * (2 * kSlicePitch);
+        const float2 a0 = c[0], b0 = c[1], d0 = c[kSlicePitch], e0 = c[kSlicePitch + 1];
+        const float2 a1 = c[2 * kSlicePitch], b1 = c[2 * kSlicePitch + 1], d1 = c[3 * kSlicePitch], e1 = c[3 * kSlicePitch + 1];
         // lerp nest x -> y -> z exactly as generator :59-64
         const float v0 = hl::lerpf(hl::lerpf(hl::lerpf(a0.x, b0.x, xf), hl::lerpf(d0.x, e0.x, xf), yf),
                                    hl::lerpf(hl::lerpf(a1.x, b1.x, xf), hl::lerpf(d1.x, e1.x, xf), yf), zf);
@@ -277,7 +283,7 @@ int run_bilateral_grid(halide_buffer_t *input, float r_sigma, halide_buffer_t *o
         HB_LAUNCH("bg_blur_xy", bg_blur_xy_kernel, g2, 256, 0, s, p, rows);
         const int tx0 = ox & ~(S - 1), ty0 = oy & ~(S - 1);
         dim3 g3((ox + W - tx0 + kSliceW - 1) / kSliceW, (oy + H - ty0 + S - 1) / S);
-        const size_t slice_smem = (size_t)p.nz * 2 * kSliceCells * sizeof(float2);
+        const size_t slice_smem = (size_t)p.nz * 2 * kSlicePitch * sizeof(float2);
         if (slice_smem > 48 * 1024) cudaFuncSetAttribute(bg_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slice_smem);
         HB_LAUNCH("bg_slice", bg_slice_kernel, g3, dim3(32, 8), slice_smem, s, p);
     }

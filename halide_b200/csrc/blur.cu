@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) blur3x3_u16_kernel(BlurAr
 // One warp = a 128-pixel-wide strip walked top to bottom with the last two blur_x rows in registers and kQuadAhead
 // input rows in flight per lane; the strip height is chosen on the host so that the strips fill the resident warps of
 // the device a whole number of times (no tail wave).
-constexpr int kQuadAhead = 6, kQuadWarps = 4, kQuadW = 128;
+constexpr int kQuadWarps = 4, kQuadW = 128;  // (kQuadAhead: template parameter AHEAD, a multiple of 3 so the row window rotates by renaming)
 constexpr uint32_t kThird = 0x55555556u;
 
 __device__ __forceinline__ uint32_t ld_pair(const BlurArgs &a, int64_t off) {  // off even: one aligned word, or guarded halves
@@ -199,7 +199,7 @@ __device__ __forceinline__ void blur_x_quad(const QuadRow &q, uint32_t (&b)[4]) 
 // Walks one strip.  `rin` is the row pointer of the next input row to request, `rout` the output row pointer.  The
 // bulk of the strip runs without any test per row; only the refills of the last rows (which would run past the
 // strip's last input row) use the clamped request, which re-requests a valid row.
-template<bool GUARD>
+template<bool GUARD, int kQuadAhead>
 struct QuadStrip {
     const BlurArgs &a;
     const uint16_t *rin;
@@ -269,6 +269,7 @@ struct QuadStrip {
 };
 
 // a.rows_per_warp = strip height; strips are numbered x-fastest so the warps of a block read adjacent spans of a row
+template<int AHEAD>
 __global__ void __launch_bounds__(32 * kQuadWarps) blur3x3_u16_quad_kernel(BlurArgs a, int strips_x, int strips) {
     const int lane = threadIdx.x & 31;
     const int t = blockIdx.x * kQuadWarps + (threadIdx.x >> 5);
@@ -278,11 +279,11 @@ __global__ void __launch_bounds__(32 * kQuadWarps) blur3x3_u16_quad_kernel(BlurA
     const int y1 = min(y0 + a.rows_per_warp, a.h);
     // whole strip (and the two input columns to its right) inside the output width: nothing to guard
     if (xw + kQuadW <= a.w) {
-        QuadStrip<false> st{a};
+        QuadStrip<false, AHEAD> st{a};
         st.x = xw + 4 * lane;
         st.run(y0, y1);
     } else {
-        QuadStrip<true> st{a};
+        QuadStrip<true, AHEAD> st{a};
         st.x = xw + 4 * lane;
         st.run(y0, y1);
     }
@@ -363,12 +364,13 @@ extern "C" int halide_blur(halide_buffer_t *input, halide_buffer_t *blur_y) {
         hb::CallTimer timer(s);
         if (pair_ok) {
             // strips of 128 columns; height such that the strips fill the resident warps a whole number of times
+            // (six rows in flight per lane: nine — 86 registers, five blocks per SM — measured slower, 33.5 vs 29.3 us at 8K)
             static int resident = 0;  // blocks per SM x SMs (per process: one device per process)
             if (!resident) {
                 int per_sm = 0, dev = 0, sms = 0;
                 cudaGetDevice(&dev);
                 cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blur3x3_u16_quad_kernel, 32 * kQuadWarps, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blur3x3_u16_quad_kernel<6>, 32 * kQuadWarps, 0);
                 resident = (per_sm > 0 ? per_sm : 8) * (sms > 0 ? sms : 148);
             }
             const int sxq = (w + kQuadW - 1) / kQuadW;
@@ -386,8 +388,8 @@ extern "C" int halide_blur(halide_buffer_t *input, halide_buffer_t *blur_y) {
             if (g_force_general >= 8) qrows = g_force_general;
             a.rows_per_warp = qrows;
             const int strips_q = sxq * ((h + qrows - 1) / qrows);
-            HB_LAUNCH("blur3x3_u16_quad", blur3x3_u16_quad_kernel, (strips_q + kQuadWarps - 1) / kQuadWarps, 32 * kQuadWarps, 0, s, a,
-                      sxq, strips_q);
+            const int nblk = (strips_q + kQuadWarps - 1) / kQuadWarps;
+            HB_LAUNCH("blur3x3_u16_quad", blur3x3_u16_quad_kernel<6>, nblk, 32 * kQuadWarps, 0, s, a, sxq, strips_q);
         } else {
             HB_LAUNCH("blur3x3_u16", blur3x3_u16_kernel, grid, 32 * kWarpsPerBlock, 0, s, a);
         }
