@@ -371,40 +371,43 @@ def run_ours(args, rank, world, local_rank):
     e2e = {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world,
            "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "host_memory": "pinned",
            "mode": "one caller thread per rank: H2D, kernels, D2H back to back (the same form at every N)"}
-    if world == 1 and nbytes < 200_000_000:
+    if world == 1:
         # Context only (not `e2e.value`): a caller with several frames in hand (video) keeps DEPTH frames in flight, one
         # thread + CUDA stream each (halide_b200.FramePipeline): every step still copies its own input up and its own
         # result down, but frame i's D2H overlaps frame i+1's kernels and frame i+2's H2D on the full-duplex link.
         from halide_b200 import FramePipeline
-        DEPTH = 3
-        slots = []
-        for k in range(DEPTH):
-            hi = torch.empty((3, band_h, W), dtype=torch.uint16).pin_memory()
-            hi.view(torch.int16).copy_(ins[k % NSETS].view(torch.int16))
-            ho = torch.empty((3, band_h, W), dtype=torch.uint16).pin_memory()
-            bi, bo = HalideBuffer.from_torch(hi), HalideBuffer.from_torch(ho)
-            bo.set_host_dirty(False)
-            slots.append((bi, bo, hi, ho))
+        try:
+            DEPTH = 3 if nbytes < 200_000_000 else 2   # (a 16K frame in flight = 3.2 GB of pinned host memory + ~8 GB of device scratch)
+            slots = []
+            for k in range(DEPTH):
+                hi = torch.empty((3, band_h, W), dtype=torch.uint16).pin_memory()
+                hi.view(torch.int16).copy_(ins[k % NSETS].view(torch.int16))
+                ho = torch.empty((3, band_h, W), dtype=torch.uint16).pin_memory()
+                bi, bo = HalideBuffer.from_torch(hi), HalideBuffer.from_torch(ho)
+                bo.set_host_dirty(False)
+                slots.append((bi, bo, hi, ho))
 
-        def job(k):
-            bi, bo = slots[k][0], slots[k][1]
-            bi.set_host_dirty(True)
-            filters.local_laplacian(bi, LEVELS, ALPHA, BETA, bo)
-            bo.copy_to_host()
+            def job(k):
+                bi, bo = slots[k][0], slots[k][1]
+                bi.set_host_dirty(True)
+                filters.local_laplacian(bi, LEVELS, ALPHA, BETA, bo)
+                bo.copy_to_host()
 
-        pipe_steps = 3 * e2e_steps
-        with FramePipeline(DEPTH, device=local_rank) as fp:
-            for t in [fp.submit(job, k % DEPTH, slot=k % DEPTH) for k in range(2 * DEPTH)]:
-                fp.result(t)
-            t0 = time.perf_counter()
-            for t in [fp.submit(job, k % DEPTH, slot=k % DEPTH) for k in range(pipe_steps)]:
-                fp.result(t)
-            e2e_pipe_s = (time.perf_counter() - t0) / pipe_steps
-        # the pipelined frames must be the same bits as the serial call's
-        if not torch.equal(slots[0][3].view(torch.int16), h_out.view(torch.int16)):
-            raise SystemExit("bench: pipelined e2e output differs from the serial call")
-        e2e["pipelined"] = {"value": total_px / 1e6 / e2e_pipe_s, "ms_per_step": e2e_pipe_s * 1e3, "steps": pipe_steps,
-                            "mode": "FramePipeline depth %d: %d caller threads, one CUDA stream each" % (DEPTH, DEPTH)}
+            pipe_steps = 3 * e2e_steps if nbytes < 200_000_000 else 8
+            with FramePipeline(DEPTH, device=local_rank) as fp:
+                for t in [fp.submit(job, k % DEPTH, slot=k % DEPTH) for k in range(2 * DEPTH)]:
+                    fp.result(t)
+                t0 = time.perf_counter()
+                for t in [fp.submit(job, k % DEPTH, slot=k % DEPTH) for k in range(pipe_steps)]:
+                    fp.result(t)
+                e2e_pipe_s = (time.perf_counter() - t0) / pipe_steps
+            # the pipelined frames must be the same bits as the serial call's
+            if not torch.equal(slots[0][3].view(torch.int16), h_out.view(torch.int16)):
+                raise SystemExit("bench: pipelined e2e output differs from the serial call")
+            e2e["pipelined"] = {"value": total_px / 1e6 / e2e_pipe_s, "ms_per_step": e2e_pipe_s * 1e3, "steps": pipe_steps,
+                                "mode": "FramePipeline depth %d: %d caller threads, one CUDA stream each" % (DEPTH, DEPTH)}
+        except (RuntimeError, MemoryError) as exc:   # (out of pinned / device memory: the serial number above stands)
+            e2e["pipelined"] = {"error": str(exc)[:300]}
 
     # ---- per-kernel profile for the roofline (event-bracketed launches, separate pass) --------------
     roofline, kernels = None, {}

@@ -268,10 +268,9 @@ int run_bilateral_grid(halide_buffer_t *input, float r_sigma, halide_buffer_t *o
     cudaStream_t s = hb::stream();
     {
         hb::CallTimer timer(s);
-        static bool attr_set = false;
-        if (bins_bytes > 48 * 1024 && !attr_set) {
-            cudaFuncSetAttribute(bg_hist_blurz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr_set = true;
+        static hb::PerDeviceOnce hist_attr;
+        if (bins_bytes > 48 * 1024) {
+            hist_attr.run([] { cudaFuncSetAttribute(bg_hist_blurz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
         }
         dim3 g1((p.gw + 63) / 64, p.gh);
         HB_LAUNCH("bg_hist_blurz", bg_hist_blurz_kernel, g1, 128, bins_bytes, s, p);

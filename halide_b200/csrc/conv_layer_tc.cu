@@ -280,12 +280,11 @@ int conv_layer_tc_run(const float *din, const float *df, const float *db, float 
         make_map(enc, &mb_hi, b_hi, 9 * CO, nt) || make_map(enc, &mb_lo, b_lo, 9 * CO, nt)) {
         return hb::fail(halide_error_code_generic_error, "conv_layer: cuTensorMapEncodeTiled failed");
     }
-    static bool attr = false;
-    if (!attr) {
+    static hb::PerDeviceOnce attr;
+    attr.run([] {
         cudaFuncSetAttribute(conv_layer_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM_BYTES);
         cudaFuncSetAttribute(conv_layer_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES);
-        attr = true;
-    }
+    });
     HB_LAUNCH("conv_split_input", conv_split_input_kernel, (unsigned)((a_elems / 4 + 255) / 256), 256, 0, s, (const float4 *)din, (float4 *)a_hi,
               (float4 *)a_lo, a_elems / 4);
     HB_LAUNCH("conv_prep_filter", conv_prep_filter_kernel, (unsigned)((b_elems + 255) / 256), 256, 0, s, df, b_hi, b_lo);

@@ -34,6 +34,21 @@ struct CallTimer {
     cudaStream_t s;
 };
 
+// ---- once-per-device set-up (function attributes are per device / context; keyed by the CURRENT device, and safe
+// to race: two threads at worst both run `fn`, which must be idempotent) -----------------------------------------
+struct PerDeviceOnce {
+    unsigned long long done = 0;  // bit d = device d set up (devices >= 64: always run fn)
+    template<typename F>
+    void run(F fn) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const unsigned long long bit = dev < 64 ? 1ull << dev : 0ull;
+        if (bit && (__atomic_load_n(&done, __ATOMIC_ACQUIRE) & bit)) return;
+        fn();
+        if (bit) __atomic_fetch_or(&done, bit, __ATOMIC_RELEASE);
+    }
+};
+
 // ---- device scratch (callee-owned intermediates; pooled, src/runtime/cuda.cpp:760-870 analogue) ---
 void *scratch_alloc(size_t bytes);  // returns nullptr on failure (caller maps to -16)
 void scratch_free(void *p);         // stream-ordered: safe to call right after the last launch

@@ -201,11 +201,8 @@ int run_nl_means(halide_buffer_t *input, int patch_size, int search_area, float 
     cudaStream_t s = hb::stream();
     {
         hb::CallTimer timer(s);
-        static size_t attr = 0;
-        if (smem > 48 * 1024 && smem > attr) {
-            cudaFuncSetAttribute(nl_means_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr = smem;
-        }
+        // (the limit is per device; setting it is cheap, so it is simply set for every call that needs it)
+        if (smem > 48 * 1024) cudaFuncSetAttribute(nl_means_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         dim3 grid((W + TX - 1) / TX, (H + TY - 1) / TY);
         HB_LAUNCH("nl_means", nl_means_kernel, grid, 256, smem, s, q);
     }
