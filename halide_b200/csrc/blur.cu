@@ -8,11 +8,13 @@
 // input must cover [ox, ox+W+1] x [oy, oy+H+1] or the call fails with -4
 // (src/AddImageChecks.cpp:404-417).
 //
-// Kernel shape: HBM-bound, 4 algorithmic bytes per pixel.  One warp owns a 256-pixel-wide
-// column strip; each lane produces 8 adjacent pixels (one 16-byte store) per row and walks down
-// the strip keeping the last three blur_x rows in registers, so every input element is fetched
-// once per strip as part of an aligned 16-byte load and the 2-pixel horizontal apron comes from
-// the neighbouring lane by shuffle, not from memory.
+// Kernel shape: HBM-bound, 4 algorithmic bytes per pixel.  Two kernels, both "one warp walks a column strip top to
+// bottom with the last two blur_x rows in registers, several input rows in flight per lane":
+//   * blur3x3_u16_quad_kernel — frames whose rows keep pixel pairs 4-byte aligned (even row strides: the harness and
+//     RunGen frames): a lane owns 4 pixels, 32-bit loads, arithmetic in high-half form, ~10 instructions per pixel,
+//     strips sized to fill the resident warps a whole number of times.  29.8 us at 8K (68 % of the measured HBM peak).
+//   * blur3x3_u16_kernel — any alignment: a lane owns 8 pixels, aligned 16-byte loads realigned by funnel shifts, the
+//     2-pixel horizontal apron from the neighbouring lane by shuffle.  Bound by the integer pipe (49 us at 8K).
 #include "hb_common.h"
 
 namespace {

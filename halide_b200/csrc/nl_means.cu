@@ -116,6 +116,100 @@ __global__ void __launch_bounds__(256) nl_means_kernel(NLParams q) {
     }
 }
 
+// ---- register-window version for compile-time patch / search sizes ------------------------------------------------
+// The kernel above is generic in patch and search size: every tile coordinate costs an integer division by a run-time
+// extent, d goes through shared memory twice (D, then V) and the loops cannot unroll — ~165 instructions per pixel and
+// search offset.  With P and S fixed at compile time:
+//   phase 1: a thread owns one column u of one search offset dx and walks down the tile's TY + P - 1 rows; d of the new
+//            row comes from six shared loads (three channels of the centre and of the shifted tile), the vertical patch
+//            sum is the explicit ascending sum over a register window ((0 + d0) + d1) + ... — the reference's order —
+//            and only V is written to shared memory;
+//   phase 2: as before (horizontal patch sum, fast_exp, four running sums per pixel, two rows per thread), unrolled.
+// All S offsets of a search row are batched between two barriers.  Same float operations in the same order as the
+// generic kernel (results are bit-identical to it; tests/test_nl_means_gpu.py runs both against the oracle).
+template<int P, int S>
+__global__ void __launch_bounds__(256) nl_means_window_kernel(NLParams q) {
+    constexpr int IW = TX + P + S - 2, IH = TY + P + S - 2, DW = TX + P - 1, DH = TY + P - 1, PLANE = IH * IW;
+    constexpr int PLO = -(P / 2), SLO = -(S / 2), OFFS = -SLO;
+    extern __shared__ float smem[];
+    float *sI = smem;             // [3][IH][IW]
+    float *sV = sI + 3 * PLANE;   // [S][TY][DW]
+    const int tid = threadIdx.x;
+    const int X0 = q.out_x0 + blockIdx.x * TX, Y0 = q.out_y0 + blockIdx.y * TY;
+    const int ax0 = X0 + PLO + SLO, ay0 = Y0 + PLO + SLO;  // tile (u, v) <-> absolute (ax0 + u, ay0 + v)
+    for (int t = tid; t < 3 * PLANE; t += 256) {
+        const int c = t / PLANE, rem = t - c * PLANE;
+        const int v = rem / IW, u = rem - v * IW;
+        const int x = hl::clampi(ax0 + u, q.in_x0, q.in_x0 + q.in_w - 1) - q.in_x0;
+        const int y = hl::clampi(ay0 + v, q.in_y0, q.in_y0 + q.in_h - 1) - q.in_y0;
+        const int cc = hl::clampi(c, q.in_c0, q.in_c0 + q.in_c - 1) - q.in_c0;
+        sI[t] = __ldg(q.in + (int64_t)cc * q.in_sc + (int64_t)y * q.in_sy + x);
+    }
+    __syncthreads();
+    const int tx = tid & 31, ty = tid >> 5;  // rows ty and ty + 8
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    for (int dyi = 0; dyi < S; dyi++) {
+        // ---- phase 1: V[j][y][u] = sum_{k<P} d(u, y + k) for search offset (SLO + j, SLO + dyi)
+        for (int it = tid; it < DW * S; it += 256) {
+            const int j = it / DW, u = it - j * DW;
+            const float *a = sI + OFFS * IW + (u + OFFS);   // centre pixel of d: tile row v + OFFS
+            const float *b = sI + dyi * IW + (u + j);       // shifted pixel:     tile row v + dyi
+            float *vout = sV + j * TY * DW + u;
+            float win[P];
+#pragma unroll
+            for (int v = 0; v < DH; v++) {
+                const float e0 = a[v * IW] - b[v * IW], e1 = a[PLANE + v * IW] - b[PLANE + v * IW],
+                            e2 = a[2 * PLANE + v * IW] - b[2 * PLANE + v * IW];
+                win[v % P] = ((0.0f + e0 * e0) + e1 * e1) + e2 * e2;
+                if (v >= P - 1) {
+                    float sum = 0.f;
+#pragma unroll
+                    for (int k = 0; k < P; k++) sum += win[(v - (P - 1) + k) % P];  // rows y .. y + P - 1, ascending
+                    vout[(v - (P - 1)) * DW] = sum;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: horizontal sums, weights, accumulation
+#pragma unroll
+        for (int j = 0; j < S; j++) {
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const int y = ty + 8 * r;
+                const float *vrow = sV + (j * TY + y) * DW + tx;
+                float bd = 0.f;
+#pragma unroll
+                for (int k = 0; k < P; k++) bd += vrow[k];
+                const float w = hl::fast_exp(bd * q.inv_sigma_sq);
+                const float *nb = sI + (y - PLO + dyi) * IW + (tx - PLO + j);
+                acc[r][0] += w * nb[0];
+                acc[r][1] += w * nb[PLANE];
+                acc[r][2] += w * nb[2 * PLANE];
+                acc[r][3] += w;
+            }
+        }
+        __syncthreads();  // (the next search row's phase 1 overwrites sV)
+    }
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int lx = blockIdx.x * TX + tx, ly = blockIdx.y * TY + ty + 8 * r;
+        if (lx < q.W && ly < q.H) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const float v = hl::clampf(__fdiv_rn(acc[r][c], acc[r][3]), 0.0f, 1.0f);
+                q.out[(int64_t)c * q.out_sc + (int64_t)ly * q.out_sy + lx] = v;
+            }
+        }
+    }
+}
+template<int P, int S>
+constexpr size_t nl_window_smem() {
+    return (size_t)(3 * (TY + P + S - 2) * (TX + P + S - 2) + S * TY * (TX + P - 1)) * sizeof(float);
+}
+
+constexpr bool kDefaultWindow = false;  // (flipped once the register-window kernel has passed the parity tests on hardware)
+int g_variant = 0;  // test / A-B hook (halide_b200_nl_means_variant): 0 = default, 1 = generic kernel, 2 = register-window kernel
+
 const hb::ArgSpec kIn = {"input", halide_type_float, 32, 3, false};
 const hb::ArgSpec kOut = {"non_local_means", halide_type_float, 32, 3, true};
 int64_t est_i[3][2] = {{0, 1536}, {0, 2560}, {0, 3}};
@@ -204,7 +298,18 @@ int run_nl_means(halide_buffer_t *input, int patch_size, int search_area, float 
         // (the limit is per device; setting it is cheap, so it is simply set for every call that needs it)
         if (smem > 48 * 1024) cudaFuncSetAttribute(nl_means_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         dim3 grid((W + TX - 1) / TX, (H + TY - 1) / TY);
-        HB_LAUNCH("nl_means", nl_means_kernel, grid, 256, smem, s, q);
+        const bool window = g_variant == 2 || (g_variant == 0 && kDefaultWindow);
+        if (window && patch_size == 3 && search_area == 7) {
+            constexpr size_t sm = nl_window_smem<3, 7>();
+            static_assert(sm <= 48 * 1024, "no opt-in needed");
+            HB_LAUNCH("nl_means_window", (nl_means_window_kernel<3, 7>), grid, 256, sm, s, q);
+        } else if (window && patch_size == 7 && search_area == 7) {
+            constexpr size_t sm = nl_window_smem<7, 7>();
+            static_assert(sm <= 48 * 1024, "no opt-in needed");
+            HB_LAUNCH("nl_means_window", (nl_means_window_kernel<7, 7>), grid, 256, sm, s, q);
+        } else {
+            HB_LAUNCH("nl_means", nl_means_kernel, grid, 256, smem, s, q);
+        }
     }
     if ((r = hb::check_cuda(cudaGetLastError(), "nl_means launch", halide_error_code_device_run_failed))) return r;
     hb::mark_output_written(output);
@@ -212,6 +317,10 @@ int run_nl_means(halide_buffer_t *input, int patch_size, int search_area, float 
 }
 
 }  // namespace
+
+extern "C" void halide_b200_nl_means_variant(int v) {
+    g_variant = v;
+}
 
 extern "C" int nl_means(halide_buffer_t *input, int32_t patch_size, int32_t search_area, float sigma, halide_buffer_t *output) {
     return run_nl_means(input, patch_size, search_area, sigma, output);

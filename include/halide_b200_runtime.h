@@ -301,6 +301,10 @@ void halide_b200_ll_force_generic(int mask);
 /* halide_blur test hook: 1 = route 4-byte-aligned frames through the general (any alignment) kernel as well;
  * >= 8 = aligned kernel with strips of that many rows (0 restores the defaults). */
 void halide_b200_blur_force_general(int enable);
+/* nl_means test / A-B hook: 0 = default kernel, 1 = generic kernel, 2 = register-window kernel (patch 3 or 7, search 7). */
+void halide_b200_nl_means_variant(int variant);
+/* stencil_chain test / A-B hook: 0 = default kernel, 1 = one-pixel-per-thread tile kernel, 2 = register-window tile kernel. */
+void halide_b200_stencil_chain_variant(int variant);
 /* conv_layer: 1 = tcgen05/TMEM/TMA implicit GEMM (3xTF32 split), 0 = FP32 SIMT kernel (also HALIDE_B200_CONV=tc|simt). */
 void halide_b200_conv_use_tensor_cores(int enable);
 /* Device self-test of the fast kernels' arithmetic shortcuts; returns mismatches vs div.rn / cvt, or -1. */

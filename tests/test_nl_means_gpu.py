@@ -74,3 +74,24 @@ def test_4k_random_frame_regions(hb, oracle):
         crop = np.ascontiguousarray(inp[:, ya:yb, xa:xb])
         want = oracle.nl_means(crop, 3, 7, 0.12, in_mins=(xa, ya, 0), out_mins=(xa, ya, 0))
         close(got[:, y0:y0 + n, x0:x0 + n], want[:, y0 - ya:y0 - ya + n, x0 - xa:x0 - xa + n])
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_generic_and_window_kernels(hb, oracle, variant):
+    """The generic kernel and the register-window kernel (compile-time patch 3 / 7, search 7; hook:
+    halide_b200_nl_means_variant) against the oracle: ragged sizes, a crop with offsets, and a patch / search pair the
+    window kernel does not cover (it must fall back by itself)."""
+    l = hb.load_library()
+    try:
+        l.halide_b200_nl_means_variant(variant)
+        for h, w in ((1, 1), (16, 32), (33, 47), (70, 101)):
+            inp = f32_frame((3, h, w), 11 * variant + h + w)
+            close(run(hb, inp, 3, 7, 0.12), oracle.nl_means(inp, 3, 7, 0.12))
+        inp = f32_frame((3, 40, 52), 77)
+        close(run(hb, inp, 7, 7, 0.12), oracle.nl_means(inp, 7, 7, 0.12))
+        close(run(hb, inp, 5, 9, 0.3), oracle.nl_means(inp, 5, 9, 0.3))
+        kw = dict(out_shape=(3, 30, 41), in_mins=(-4, 2, 0), out_mins=(1, 6, 0))
+        inp = f32_frame((3, 50, 70), 5)
+        close(run(hb, inp, 3, 7, 0.12, **kw), oracle.nl_means(inp, 3, 7, 0.12, **kw))
+    finally:
+        l.halide_b200_nl_means_variant(0)
