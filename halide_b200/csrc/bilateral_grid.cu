@@ -108,15 +108,38 @@ __global__ void __launch_bounds__(256) bg_blur_xy_kernel(BGParams p, int rows_pe
     const int y_begin = 2 + blockIdx.y * rows_per_block;
     const int y_end = min(y_begin + rows_per_block, p.gh - 2);
     if (y_begin >= y_end) return;
-    auto blurx_at = [&](int cy) -> float {
-        const float *r = p.grid_a + ((size_t)cy * p.gw + cx) * V + v;
-        return (((__ldg(r - 2 * V) + __ldg(r - V) * 4.0f) + __ldg(r) * 6.0f) + __ldg(r + V) * 4.0f) + __ldg(r + 2 * V);
+    // x-blur of one grid row at this thread's (cell, value): five loads, combined in the generator's order.  The loads of
+    // two rows are issued together (ten in flight per thread): with one row per iteration the kernel sat on its own load
+    // latency (long-scoreboard 60 % of the stall samples, DRAM 19 %: profiles/r02_blur_bilateral_ncu_b.md).
+    struct Taps {
+        float t[5];
     };
-    float a = blurx_at(y_begin - 2), b = blurx_at(y_begin - 1), c = blurx_at(y_begin), d = blurx_at(y_begin + 1);
-    for (int cy = y_begin; cy < y_end; cy++) {
-        float e = blurx_at(cy + 2);
+    auto load_taps = [&](int cy) -> Taps {
+        const float *r = p.grid_a + ((size_t)cy * p.gw + cx) * V + v;
+        Taps k;
+        k.t[0] = __ldg(r - 2 * V); k.t[1] = __ldg(r - V); k.t[2] = __ldg(r); k.t[3] = __ldg(r + V); k.t[4] = __ldg(r + 2 * V);
+        return k;
+    };
+    auto blurx = [](const Taps &k) -> float {
+        return (((k.t[0] + k.t[1] * 4.0f) + k.t[2] * 6.0f) + k.t[3] * 4.0f) + k.t[4];
+    };
+    float a, b, c, d;
+    {
+        const Taps k0 = load_taps(y_begin - 2), k1 = load_taps(y_begin - 1), k2 = load_taps(y_begin), k3 = load_taps(y_begin + 1);
+        a = blurx(k0); b = blurx(k1); c = blurx(k2); d = blurx(k3);
+    }
+    for (int cy = y_begin; cy < y_end; cy += 2) {
+        const bool two = cy + 1 < y_end;
+        const Taps k0 = load_taps(cy + 2);
+        const Taps k1 = load_taps(two ? cy + 3 : cy + 2);  // (rows up to y_end + 1 <= gh - 1 exist: the grid keeps a 2-cell border)
+        float e = blurx(k0);
         p.grid_b[((size_t)cy * p.gw + cx) * V + v] = (((a + b * 4.0f) + c * 6.0f) + d * 4.0f) + e;
         a = b; b = c; c = d; d = e;
+        if (two) {
+            e = blurx(k1);
+            p.grid_b[((size_t)(cy + 1) * p.gw + cx) * V + v] = (((a + b * 4.0f) + c * 6.0f) + d * 4.0f) + e;
+            a = b; b = c; c = d; d = e;
+        }
     }
 }
 
