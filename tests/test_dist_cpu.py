@@ -10,7 +10,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("frame_h,world", [(4320, 2), (2160 * 8, 8), (16384, 8), (2048, 2), (3000, 3)])
+@pytest.mark.parametrize("frame_h,world", [(4320, 2), (2160 * 8, 8), (16384, 8), (2048, 2), (3000, 3), (16384, 4), (16384, 5), (8191, 7),
+                                           (32768, 16)])
 def test_shard_rows_cover_every_tap(hb, frame_h, world):
     """Exchange-free row sharding (ll_geom.h: ShardLevel): the `own` rows partition every level, and the rows a rank
     computes (d) cover every tap of the rows it needs one level up, so nothing but the input halo and the gathered level
