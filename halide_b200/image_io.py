@@ -12,7 +12,8 @@ the reference header itself (``oracle/_ref/ref_image_io``, built from the header
 Array convention: a Halide image with dimensions (x, y, c, ...) is a C-contiguous numpy array of shape (..., c, y, x) —
 the layout ``HalideBuffer.from_numpy`` wraps.  Formats: ``.pgm .ppm .png .npy .tmp .mat`` (8- and 16-bit PNM / PNG,
 big-endian on disk like the reference; ``.npy`` and ``.tmp`` and ``.mat`` carry the extents in Halide order, x first,
-with a planar x-fastest payload, exactly as the reference writes them).  Not implemented: ``.jpg`` and ``.tiff``.
+with a planar x-fastest payload, exactly as the reference writes them; ``.tiff`` is write-only, as in the reference).
+Not implemented: ``.jpg``.
 PNG pixels are decoded here (zlib + the five row filters); files are written unfiltered, so bytes on disk differ from
 libpng's while every sample is identical.
 
@@ -352,20 +353,84 @@ def _load_mat(path):
 
 
 def _save_mat(arr, path):
+    """Byte for byte what the reference writes (:1916-2100): variable name from the file name, `dimensions * 4` shape bytes,
+    extents padded with 1 up to two dimensions and with 0 to an even count, payload padded to eight bytes."""
     if arr.dtype not in _MX_CLASS or arr.ndim < 2:
         raise ValueError("Unsupported image for .mat file")
     mi = {v: k for k, v in _MI.items()}[arr.dtype.type]
-    extents = _halide_extents(arr)
     payload = np.ascontiguousarray(arr).tobytes()
-    name = os.path.splitext(os.path.basename(path))[0].encode("latin1")
-
-    def element(tag, body):
-        return struct.pack("<2I", tag, len(body)) + body + b"\0" * (-len(body) % 8)
-    body = (element(6, struct.pack("<2I", _MX_CLASS[arr.dtype], 0)) + element(5, struct.pack("<%di" % len(extents), *extents)) +
-            element(1, name) + element(mi, payload))
-    header = b"MATLAB 5.0 MAT-file, produced by halide_b200".ljust(124) + struct.pack("<H", 0x0100) + b"IM"
+    if len(payload) >> 32:
+        raise ValueError("Buffer too large to save as .mat")
+    name = path[:path.rfind(".")] if "." in path else path
+    name = name[name.rfind("/") + 1:]
+    if not name or not (name[0].isascii() and name[0].isalpha()):
+        name = "v" + name
+    name = "".join(c if (c.isascii() and c.isalnum()) else "_" for c in name).encode("latin1")
+    name_size = len(name)
+    name += b"\0" * (-len(name) % 8)
+    dims = max(arr.ndim, 2)
+    padded_dims = dims + (dims & 1)
+    extents = _halide_extents(arr) + [1] * (dims - arr.ndim) + [0] * (padded_dims - dims)
+    padding = 7 - ((len(payload) - 1) & 7)
+    header = bytearray(b"MATLAB 5.0 MAT-file, produced by Halide".ljust(128))
+    header[124:126] = struct.pack("<H", 0x0100)
+    header[126:128] = b"IM"
     with open(path, "wb") as f:
-        f.write(header + struct.pack("<2I", 14, len(body)) + body)
+        f.write(bytes(header))
+        f.write(struct.pack("<2I", 14, 40 + padded_dims * 4 + len(name) + len(payload) + padding))
+        f.write(struct.pack("<4I", 6, 8, _MX_CLASS[arr.dtype], 1))
+        f.write(struct.pack("<2i", 5, arr.ndim * 4) + struct.pack("<%di" % padded_dims, *extents))
+        f.write(struct.pack("<2I", 1, name_size) + name)
+        f.write(struct.pack("<2I", mi, len(payload)) + payload + b"\0" * padding)
+
+
+# .tiff (:2109-2375): the reference only WRITES TIFF (uncompressed, one strip per channel, planar), and cannot read it
+def _save_tiff(arr, path):
+    if arr.ndim > 4 or arr.dtype.kind not in "iuf":
+        raise ValueError("Can only save TIFF files with <= 4 dimensions of an integer or float type")
+    ext = _halide_extents(arr) + [1] * (4 - arr.ndim)
+    width, height, depth, channels = ext
+    if channels in (0, 1) and depth < 5:
+        channels, depth = depth, 1
+    bpe = arr.dtype.itemsize
+    elements = int(np.prod(arr.shape))
+    header_size = 210
+    tags = []
+
+    def tag16(code, count, value):
+        tags.append(struct.pack("<HhiHH", code, 3, count, value & 0xFFFF, 0))
+
+    def tag32(code, count, value, type_code=4):
+        tags.append(struct.pack("<Hhii", code, type_code, count, value))
+    tag32(256, 1, width)
+    tag32(257, 1, height)
+    tag16(258, 1, bpe * 8)
+    tag16(259, 1, 1)
+    tag16(262, 1, 2 if channels >= 3 else 1)
+    tag32(273, channels, header_size)
+    tag16(277, 1, channels)
+    tag32(278, 1, height)
+    tag32(279, channels, elements * bpe if channels == 1 else header_size + channels * 4)
+    tag32(282, 1, 194, type_code=5)
+    tag32(283, 1, 202, type_code=5)
+    tag16(284, 1, 1 if channels == 1 else 2)
+    tag16(296, 1, 1)
+    tag16(339, 1, {"i": 2, "u": 1, "f": 3}[arr.dtype.kind])
+    tag32(32997, 1, depth)
+    header = struct.pack("<hhih", 0x4949, 42, 8, 15) + b"".join(tags) + struct.pack("<i4i", 0, 1, 1, 1, 1)
+    assert len(header) == header_size
+    with open(path, "wb") as f:
+        f.write(header)
+        if channels > 1:
+            plane = width * height * depth * bpe
+            first = header_size + channels * 4 * 2
+            f.write(struct.pack("<%di" % channels, *[first + i * plane for i in range(channels)]))
+            f.write(struct.pack("<%di" % channels, *([plane] * channels)))
+        f.write(np.ascontiguousarray(arr).tobytes())
+
+
+def _load_tiff(path):
+    raise ValueError("Reading TIFF is not yet supported")   # (the reference's words, tools/halide_image_io.h:2111)
 
 
 # .png (:867-1030 semantics: 8 / 16-bit samples as stored, no palette expansion, channels from the colour type)
@@ -497,6 +562,8 @@ def save_query(path):
         s = [(t, 4) for t in _TMP_SET]
     elif e == "mat":
         s = [(t, d) for t in _TMP_SET for d in range(2, 16)]
+    elif e in ("tiff",):
+        s = [(t, d) for t in _INT_UINT_FLOAT if t != np.float16 for d in (1, 2, 3, 4)]
     else:
         raise ValueError(f'unsupported file extension "{e}"')
     key = lambda td: ({"i": 0, "u": 1, "f": 2}[np.dtype(td[0]).kind], np.dtype(td[0]).itemsize, td[1])
@@ -519,9 +586,9 @@ def best_save_format(arr, formats):
 
 
 _LOADERS = {"pgm": lambda p: _load_pnm(p, 1), "ppm": lambda p: _load_pnm(p, 3), "png": _load_png, "npy": _load_npy,
-            "tmp": _load_tmp, "mat": _load_mat}
+            "tmp": _load_tmp, "mat": _load_mat, "tiff": _load_tiff}
 _SAVERS = {"pgm": lambda a, p: _save_pnm(a, p, 1), "ppm": lambda a, p: _save_pnm(a, p, 3), "png": _save_png,
-           "npy": _save_npy, "tmp": _save_tmp, "mat": _save_mat}
+           "npy": _save_npy, "tmp": _save_tmp, "mat": _save_mat, "tiff": _save_tiff}
 
 
 def load(path):

@@ -112,7 +112,10 @@ def random_image(dtype, shape, seed):
 @pytest.mark.parametrize("fmt,dtype,shape", FORMAT_CASES)
 def test_formats_round_trip_through_the_reference(fmt, dtype, shape, tmp_path):
     a = random_image(dtype, shape, len(shape) * 7 + np.dtype(dtype).itemsize)
-    dump, ref_file, our_file, back = (str(tmp_path / n) for n in ("a.dump", "ref." + fmt, "ours." + fmt, "b.dump"))
+    (tmp_path / "r").mkdir()
+    (tmp_path / "o").mkdir()
+    # (same base name in two directories: a .mat file carries its own file name as the variable name)
+    dump, ref_file, our_file, back = (str(tmp_path / n) for n in ("a.dump", "r/img." + fmt, "o/img." + fmt, "b.dump"))
     # the reference writes, we read
     write_dump(a, dump)
     subprocess.run([REF, "save", dump, ref_file], check=True)
@@ -122,7 +125,7 @@ def test_formats_round_trip_through_the_reference(fmt, dtype, shape, tmp_path):
     image_io.save(a, our_file)
     subprocess.run([REF, "load", our_file, back], check=True)
     assert np.array_equal(read_dump(back), a)
-    if fmt in ("pgm", "ppm", "npy", "tmp"):   # these writers are byte-for-byte the reference's
+    if fmt in ("pgm", "ppm", "npy", "tmp", "mat"):   # these writers are byte-for-byte the reference's
         assert open(our_file, "rb").read() == open(ref_file, "rb").read()
 
 
@@ -235,3 +238,19 @@ def test_reference_png_images_decode_the_same_both_ways():
             del os.environ["HALIDE_B200_PNG_PURE"]
         assert fast.dtype == pure.dtype and np.array_equal(fast, pure), name
     assert np.array_equal(image_io.load(os.path.join(images, "gray_small.png")), image_io.load(os.path.join(images, "gray_small.pgm")))
+
+
+@have_ref
+@pytest.mark.parametrize("dtype,shape", [(np.uint8, (9, 14)), (np.uint16, (3, 9, 14)), (np.float32, (4, 5, 6)), (np.int32, (7,)),
+                                         (np.float64, (2, 3, 4, 5)), (np.uint8, (6, 3, 4)), (np.int16, (1, 2, 8, 9))])
+def test_tiff_writer_is_byte_identical(dtype, shape, tmp_path):
+    """The reference writes (uncompressed, planar) TIFF and cannot read it back; ours must produce the same bytes —
+    including the rule that folds a third dimension below 5 into the channel count."""
+    a = random_image(dtype, shape, 11)
+    dump, ref_file, our_file = (str(tmp_path / n) for n in ("a.dump", "ref.tiff", "ours.tiff"))
+    write_dump(a, dump)
+    subprocess.run([REF, "save", dump, ref_file], check=True)
+    image_io.save(a, our_file)
+    assert open(our_file, "rb").read() == open(ref_file, "rb").read()
+    with pytest.raises(ValueError):
+        image_io.load(our_file)
