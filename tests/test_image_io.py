@@ -254,3 +254,29 @@ def test_tiff_writer_is_byte_identical(dtype, shape, tmp_path):
     assert open(our_file, "rb").read() == open(ref_file, "rb").read()
     with pytest.raises(ValueError):
         image_io.load(our_file)
+
+
+def test_natural_image_flow_like_process_cpp(tmp_path):
+    """apps/local_laplacian/process.cpp end to end on the host side: load_and_convert_image(png) into uint16 planes, the
+    filter (the CPU oracle stands in for it here — the GPU parity tests cover the filter itself), convert_and_save_image
+    to a 16-bit PNG, reload: the file holds exactly the filter's output, and an 8-bit source enters as x * 257."""
+    from oracle import pyoracle
+    images = "/root/reference/apps/images"
+    src = os.path.join(images, "rgb_small.png")
+    if not os.path.exists(src):
+        yy, xx = np.mgrid[0:48, 0:64]
+        rgb = np.stack([(np.sin(xx / 6.0) * 100 + 128), (np.cos(yy / 5.0) * 90 + 120), ((xx + yy) * 2 % 256)]).astype(np.uint8)
+        src = str(tmp_path / "synthetic.png")
+        image_io.save(rgb, src)
+    native = image_io.load(src)
+    assert native.dtype == np.uint8 and native.ndim == 3 and native.shape[0] == 3
+    frame = image_io.load_and_convert_image(src, np.uint16)
+    assert np.array_equal(frame, native.astype(np.uint16) * 257)
+    frame = np.ascontiguousarray(frame[:, :96, :128])   # a crop keeps the oracle quick
+    out = pyoracle.local_laplacian(frame, 8, 1.0 / 7.0, 1.0)
+    dst = str(tmp_path / "out.png")
+    image_io.convert_and_save_image(out, dst)
+    back = image_io.load(dst)
+    assert back.dtype == np.uint16 and np.array_equal(back, out)
+    image_io.convert_and_save_image(out, str(tmp_path / "out8.ppm"))   # (.ppm holds uint16 too: saved as is)
+    assert np.array_equal(image_io.load(str(tmp_path / "out8.ppm")), out)
